@@ -1,0 +1,30 @@
+"""CPU oracle for the HiC-GNN / GAT-HiC training hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``hic_gnn_b200/`` imports this package; only
+``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
+legs of ``bench.py`` may.  It is the checker, never the thing shipped or measured as the
+product.
+
+What it is: a pure torch/numpy (CPU) restatement of the reference algorithm for the path
+named in SURVEY.md section 8, each function citing the reference ``file:line`` it follows.
+
+Parity pin status:
+
+* ``convert_to_matrix``, ``load_input`` (up to the ``SparseTensor`` constructor) and
+  ``cont2dist`` are PINNED: ``tests/golden/make_golden.py`` imports the reference's own
+  ``utils.py`` in the build container (third-party ``torch_geometric`` / ``torch_sparse``
+  stubbed) and records its outputs on the shipped chr19 contact lists; the oracle is
+  checked against those vectors in ``tests/test_oracle_golden.py``.
+* KR normalisation -> ``cont2dist`` -> ``cdist`` -> MSE / Spearman is PINNED end to end by
+  the reference's shipped ``Outputs/*_structure.pdb`` + ``*_log.txt`` known answers.
+* The MLP heads of ``Net`` / the GAT nets are pinned against the reference's own
+  ``models.py`` forward (imported with the conv layer stubbed) and the shipped
+  ``Outputs/GM12878_1mb_chr19_list_weights.pt`` key/shape layout.
+* GATConv / SAGEConv aggregation / ``SparseTensor.to_symmetric`` / ``set_diag`` live in
+  un-vendored third-party wheels (torch-geometric 1.7.2, torch-sparse 0.6.11,
+  torch-scatter 2.0.8) that are absent here and that no reference test pins:
+  **parity unpinned** at that boundary.  Their published algorithms are restated in
+  ``oracle/conv.py``.
+"""
+
+from . import graph, kr, wish, conv, models, loss, loop  # noqa: F401
