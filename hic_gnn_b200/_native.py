@@ -1,0 +1,79 @@
+"""ctypes binding of the C ABI in ``include/hicgat.h`` (libhicgat_sm100.so).
+
+The library is loaded lazily on first use and there is NO fallback: if it is missing the
+call raises, it never routes to a CPU or PyTorch implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libhicgat_sm100.so")
+HEADER = os.path.join(os.path.dirname(_PKG), "include", "hicgat.h")
+
+_p, _i64, _i32, _u32, _f32, _f64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_float, C.c_double, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/hicgat.h one to one
+SIGNATURES = {
+    "hicgat_version": (C.c_int, []),
+    "hicgat_last_error": (C.c_char_p, []),
+    "hicgat_launch_count": (C.c_uint64, []),
+    "hicgat_pairloss_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "hicgat_pairloss_fwd_bwd": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _p, _sz, _p]),
+    "hicgat_pairloss_fwd_bwd_packed": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _sz, _p]),
+    "hicgat_pairloss_set_tuning": (C.c_int, [_i32, _i32]),
+    "hicgat_pairdist_fwd": (C.c_int, [_p, _i64, _p, _i64, _p]),
+    "hicgat_pairdist_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _p]),
+    "hicgat_cont2dist_max_f64": (C.c_int, [_p, _i64, _i64, _i64, _i64, _f64, _p, _p, _sz, _p]),
+    "hicgat_cont2dist_apply_f64": (C.c_int, [_p, _i64, _i64, _i64, _i64, _f64, _p, _p, _i64, _p, _i64, _p]),
+    "hicgat_cont2dist_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "hicgat_csr_count_f64": (C.c_int, [_p, _i64, _i64, _i32, _p, _p]),
+    "hicgat_csr_scan_i64": (C.c_int, [_p, _i64, _p, _p]),
+    "hicgat_csr_fill_f64": (C.c_int, [_p, _i64, _i64, _i32, _p, _p, _p, _p]),
+    "hicgat_csr_pack_i32": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p]),
+    "hicgat_csr_add_self_loops_i32": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
+    "hicgat_sage_norm_values": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
+    "hicgat_spmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p]),
+    "hicgat_csr_transpose_perm": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "hicgat_gat_fwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),
+    "hicgat_gat_bwd_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "hicgat_gat_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+}
+
+PAIR_GRAD_MSE, PAIR_GRAD_L1, PAIR_MOMENTS, PAIR_NMOM = 1, 2, 4, 8
+
+_lib = None
+
+
+def declared_symbols() -> list[str]:
+    """Every function name ``include/hicgat.h`` declares (used by the export test)."""
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"HICGAT_API\s+[\w\s\*]+?\b(hicgat_\w+)\s*\(", text)))
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m hic_gnn_b200.build` "
+                "(there is no CPU / PyTorch fallback for the hot path)"
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().hicgat_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what or 'hicgat'} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().hicgat_launch_count())

@@ -1,0 +1,530 @@
+// Message passing of the two graph-conv layers on the hot path, CSR order, warp per row.
+//
+//   SAGEConv aggregate : layers.py:75-79   out[i,:] = sum_k w_k x[col_k,:]
+//   GATConv            : torch-geometric 1.7.2 GATConv as used at models.py:619 / :1013
+//                        (SURVEY.md Appendix A.3): per-edge LeakyReLU logits, segmented softmax
+//                        with warp shuffles, vectorised gather-SpMM; backward in the same CSR
+//                        order through the transposed-entry permutation (pattern is symmetric).
+//
+// Nothing is materialised per edge except alpha / dz ([nnz, H] floats); PyG materialises
+// [nnz, H, C].  Features are read as float4: lane l owns channels q*128 + 4l .. +3 of each
+// 128-wide chunk q (Q = H*C/128 chunks), so one chunk always belongs to a single head.
+#include "common.cuh"
+
+namespace hicgat {
+namespace {
+
+constexpr int kRowsPerCta = 8;  // 8 warps, one row each
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float4& acc, float a, const float4& v) {
+    acc.x = fmaf(a, v.x, acc.x);
+    acc.y = fmaf(a, v.y, acc.y);
+    acc.z = fmaf(a, v.z, acc.z);
+    acc.w = fmaf(a, v.w, acc.w);
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+// ------------------------------------------------------------------ weighted CSR SpMM
+template <int Q>
+__global__ void __launch_bounds__(256) spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                   const float* __restrict__ w, const float* __restrict__ x, int n,
+                                                   float* __restrict__ out) {
+    constexpr int F = Q * 128;
+    const int i = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    float4 acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int rs = rowptr[i], re = rowptr[i + 1];
+    for (int base = rs; base < re; base += 32) {
+        const int k = base + lane;
+        const int myj = k < re ? col[k] : 0;
+        const float myw = k < re ? w[k] : 0.f;
+        const int cnt = min(32, re - base);
+        for (int t = 0; t < cnt; t += 4) {
+            int j[4];
+            float a[4];
+            float4 v[4][Q];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                j[u] = __shfl_sync(0xffffffffu, myj, (t + u) & 31);
+                a[u] = __shfl_sync(0xffffffffu, myw, (t + u) & 31);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) v[u][q] = ldg_f4(x + (size_t)j[u] * F + q * 128 + lane * 4);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) fma4(acc[q], a[u], v[u][q]);
+                }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) *reinterpret_cast<float4*>(out + (size_t)i * F + q * 128 + lane * 4) = acc[q];
+}
+
+// ------------------------------------------------------------------ GAT: logit halves
+// a_src[i,h] = <xl[i,h,:], att_l[h,:]>, a_dst[i,h] = <xl[i,h,:], att_r[h,:]>
+template <int H, int Q>
+__global__ void __launch_bounds__(256) gat_logit_kernel(const float* __restrict__ xl, const float* __restrict__ att_l,
+                                                        const float* __restrict__ att_r, int n, float* __restrict__ a_src,
+                                                        float* __restrict__ a_dst) {
+    constexpr int F = Q * 128, QH = Q / H;
+    const int i = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    float sl[H], sr[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) sl[h] = sr[h] = 0.f;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const float4 v = ldg_f4(xl + (size_t)i * F + q * 128 + lane * 4);
+        sl[q / QH] += dot4(v, ldg_f4(att_l + q * 128 + lane * 4));
+        sr[q / QH] += dot4(v, ldg_f4(att_r + q * 128 + lane * 4));
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const float l = warp_sum(sl[h]), r = warp_sum(sr[h]);
+        if (lane == 0) {
+            a_src[i * H + h] = l;
+            a_dst[i * H + h] = r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ GAT forward
+template <int H, int Q>
+__global__ void __launch_bounds__(256) gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                      const float* __restrict__ xl, const float* __restrict__ a_src,
+                                                      const float* __restrict__ a_dst, const float* __restrict__ bias,
+                                                      float slope, int n, float* __restrict__ alpha, float* __restrict__ out) {
+    constexpr int F = Q * 128, QH = Q / H;
+    const int i = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int rs = rowptr[i], re = rowptr[i + 1];
+    float adst[H], m[H], s[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        adst[h] = a_dst[i * H + h];
+        m[h] = -INFINITY;
+        s[h] = 0.f;
+    }
+    // pass 1: row max of leaky_relu(a_src[j] + a_dst[i])
+    for (int k = rs + lane; k < re; k += 32) {
+        const int j = col[k];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            float z = a_src[j * H + h] + adst[h];
+            z = z > 0.f ? z : z * slope;
+            m[h] = fmaxf(m[h], z);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) m[h] = warp_max(m[h]);
+    // pass 2: p = exp(e - max), row sum; park p in alpha
+    for (int k = rs + lane; k < re; k += 32) {
+        const int j = col[k];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            float z = a_src[j * H + h] + adst[h];
+            z = z > 0.f ? z : z * slope;
+            const float p = expf(z - m[h]);
+            s[h] += p;
+            alpha[(size_t)k * H + h] = p;
+        }
+    }
+    float inv[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) inv[h] = 1.0f / (warp_sum(s[h]) + 1e-16f);
+    // pass 3: normalise, save alpha, gather-SpMM in CSR order
+    float4 acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = rs; base < re; base += 32) {
+        const int k = base + lane;
+        int myj = 0;
+        float mya[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) mya[h] = 0.f;
+        if (k < re) {
+            myj = col[k];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                mya[h] = alpha[(size_t)k * H + h] * inv[h];
+                alpha[(size_t)k * H + h] = mya[h];
+            }
+        }
+        const int cnt = min(32, re - base);
+        for (int t = 0; t < cnt; t += 4) {
+            int j[4];
+            float a[4][H];
+            float4 v[4][Q];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                j[u] = __shfl_sync(0xffffffffu, myj, (t + u) & 31);
+#pragma unroll
+                for (int h = 0; h < H; ++h) a[u][h] = __shfl_sync(0xffffffffu, mya[h], (t + u) & 31);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) v[u][q] = ldg_f4(xl + (size_t)j[u] * F + q * 128 + lane * 4);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) fma4(acc[q], a[u][q / QH], v[u][q]);
+                }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const float4 b = ldg_f4(bias + q * 128 + lane * 4);
+        float4 o = acc[q];
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        *reinterpret_cast<float4*>(out + (size_t)i * F + q * 128 + lane * 4) = o;
+    }
+}
+
+// ------------------------------------------------------------------ GAT backward, step 1 (per target row i)
+// da_k = <g_i, xl_j>_head ; de_k = a_k (da_k - sum_k' a_k' da_k') ; dz_k = de_k * leaky'(z_k)
+// outputs dz [nnz,H] and d_a_dst[i,h] = sum_k dz_k
+template <int H, int Q>
+__global__ void __launch_bounds__(256) gat_bwd_edge_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                           const float* __restrict__ xl, const float* __restrict__ a_src,
+                                                           const float* __restrict__ a_dst, const float* __restrict__ alpha,
+                                                           const float* __restrict__ gout, float slope, int n,
+                                                           float* __restrict__ dz, float* __restrict__ d_a_dst) {
+    constexpr int F = Q * 128, QH = Q / H;
+    const int i = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int rs = rowptr[i], re = rowptr[i + 1];
+    float4 g[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) g[q] = ldg_f4(gout + (size_t)i * F + q * 128 + lane * 4);
+    float dotsum[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) dotsum[h] = 0.f;
+    // pass 1: da_k for every entry (all lanes cooperate on one entry; 2 entries in flight)
+    for (int base = rs; base < re; base += 32) {
+        const int k = base + lane;
+        const int myj = k < re ? col[k] : 0;
+        const int cnt = min(32, re - base);
+        float myda[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) myda[h] = 0.f;
+        for (int t = 0; t < cnt; t += 2) {
+            float4 v[2][Q];
+            int j[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) j[u] = __shfl_sync(0xffffffffu, myj, (t + u) & 31);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (t + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) v[u][q] = ldg_f4(xl + (size_t)j[u] * F + q * 128 + lane * 4);
+                }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (t + u < cnt) {
+                    float part[H];
+#pragma unroll
+                    for (int h = 0; h < H; ++h) part[h] = 0.f;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) part[q / QH] += dot4(g[q], v[u][q]);
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        const float d = warp_sum(part[h]);
+                        if (lane == t + u) myda[h] = d;
+                    }
+                }
+        }
+        if (k < re) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                dz[(size_t)k * H + h] = myda[h];
+                dotsum[h] += alpha[(size_t)k * H + h] * myda[h];
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) dotsum[h] = warp_sum(dotsum[h]);
+    // pass 2: softmax + leaky-relu backward
+    float adst[H], sdst[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        adst[h] = a_dst[i * H + h];
+        sdst[h] = 0.f;
+    }
+    for (int k = rs + lane; k < re; k += 32) {
+        const int j = col[k];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float a = alpha[(size_t)k * H + h];
+            const float de = a * (dz[(size_t)k * H + h] - dotsum[h]);
+            const float z = a_src[j * H + h] + adst[h];
+            const float d = z > 0.f ? de : de * slope;
+            dz[(size_t)k * H + h] = d;
+            sdst[h] += d;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const float t = warp_sum(sdst[h]);
+        if (lane == 0) d_a_dst[i * H + h] = t;
+    }
+}
+
+// ------------------------------------------------------------------ GAT backward, step 2 (per source row j)
+// dxl[j,:] = sum_{i in N(j)} a_ij g_i + d_a_src[j] att_l + d_a_dst[j] att_r ; d_a_src[j,h] = sum_i dz_ij
+// entry k' = (j,i) of row j <-> transposed entry perm[k'] = (i,j)
+template <int H, int Q>
+__global__ void __launch_bounds__(256) gat_bwd_node_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                           const int32_t* __restrict__ perm, const float* __restrict__ alpha,
+                                                           const float* __restrict__ dz, const float* __restrict__ gout,
+                                                           const float* __restrict__ att_l, const float* __restrict__ att_r,
+                                                           const float* __restrict__ d_a_dst, int n, float* __restrict__ d_a_src,
+                                                           float* __restrict__ dxl) {
+    constexpr int F = Q * 128, QH = Q / H;
+    const int jn = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (jn >= n) return;
+    const int rs = rowptr[jn], re = rowptr[jn + 1];
+    float4 acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ssrc[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) ssrc[h] = 0.f;
+    for (int base = rs; base < re; base += 32) {
+        const int k = base + lane;
+        int myi = 0;
+        float mya[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) mya[h] = 0.f;
+        if (k < re) {
+            myi = col[k];
+            const int kt = perm[k];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                mya[h] = alpha[(size_t)kt * H + h];
+                ssrc[h] += dz[(size_t)kt * H + h];
+            }
+        }
+        const int cnt = min(32, re - base);
+        for (int t = 0; t < cnt; t += 4) {
+            int ii[4];
+            float a[4][H];
+            float4 v[4][Q];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ii[u] = __shfl_sync(0xffffffffu, myi, (t + u) & 31);
+#pragma unroll
+                for (int h = 0; h < H; ++h) a[u][h] = __shfl_sync(0xffffffffu, mya[h], (t + u) & 31);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) v[u][q] = ldg_f4(gout + (size_t)ii[u] * F + q * 128 + lane * 4);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) fma4(acc[q], a[u][q / QH], v[u][q]);
+                }
+        }
+    }
+    float dsrc[H], ddst[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        dsrc[h] = warp_sum(ssrc[h]);
+        ddst[h] = d_a_dst[jn * H + h];
+        if (lane == 0) d_a_src[jn * H + h] = dsrc[h];
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const float4 al = ldg_f4(att_l + q * 128 + lane * 4), ar = ldg_f4(att_r + q * 128 + lane * 4);
+        float4 o = acc[q];
+        const float s = dsrc[q / QH], d = ddst[q / QH];
+        o.x += s * al.x + d * ar.x;
+        o.y += s * al.y + d * ar.y;
+        o.z += s * al.z + d * ar.z;
+        o.w += s * al.w + d * ar.w;
+        *reinterpret_cast<float4*>(dxl + (size_t)jn * F + q * 128 + lane * 4) = o;
+    }
+}
+
+// ------------------------------------------------------------------ GAT backward, step 3 (parameter grads)
+// datt_l[c] = sum_j d_a_src[j,h(c)] xl[j,c] ; datt_r[c] = sum_j d_a_dst[j,h(c)] xl[j,c] ; dbias[c] = sum_i g[i,c]
+// stage A: per 64-row chunk partial sums (thread per channel, coalesced); stage B: the last CTA
+// adds the chunk partials in fixed order (deterministic).
+constexpr int kParamRows = 64;
+__global__ void __launch_bounds__(256) gat_bwd_param_kernel(const float* __restrict__ xl, const float* __restrict__ gout,
+                                                            const float* __restrict__ d_a_src, const float* __restrict__ d_a_dst,
+                                                            int n, int H, int C, float* __restrict__ part, unsigned* __restrict__ counter,
+                                                            float* __restrict__ datt_l, float* __restrict__ datt_r, float* __restrict__ dbias) {
+    const int F = H * C;
+    const int chunk = blockIdx.x, nchunks = gridDim.x;
+    const int r0 = chunk * kParamRows, r1 = min(r0 + kParamRows, n);
+    for (int c = threadIdx.x; c < F; c += blockDim.x) {
+        const int h = c / C;
+        float sl = 0.f, sr = 0.f, sb = 0.f;
+        for (int r = r0; r < r1; ++r) {
+            const float x = xl[(size_t)r * F + c];
+            sl = fmaf(d_a_src[r * H + h], x, sl);
+            sr = fmaf(d_a_dst[r * H + h], x, sr);
+            sb += gout[(size_t)r * F + c];
+        }
+        float* p = part + (size_t)chunk * 3 * F;
+        __stcg(p + c, sl);
+        __stcg(p + F + c, sr);
+        __stcg(p + 2 * F + c, sb);
+    }
+    __threadfence();
+    __syncthreads();
+    __shared__ unsigned s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(nchunks - 1)) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < 3 * F; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nchunks; ++k) s += __ldcg(part + (size_t)k * 3 * F + c);
+        if (c < F) datt_l[c] = s;
+        else if (c < 2 * F) datt_r[c - F] = s;
+        else dbias[c - 2 * F] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;  // self-reset for the next call
+}
+
+bool supported(int H, int C) {
+    const int F = H * C;
+    return (H == 1 || H == 2 || H == 4) && C % 128 == 0 && (F == 128 || F == 256 || F == 512 || F == 1024);
+}
+
+#define HICGAT_DISPATCH_HQ(H, C, CALL)                              \
+    do {                                                            \
+        const int q__ = (H) * (C) / 128;                            \
+        if ((H) == 1 && q__ == 1) { CALL(1, 1); }                   \
+        else if ((H) == 1 && q__ == 2) { CALL(1, 2); }              \
+        else if ((H) == 1 && q__ == 4) { CALL(1, 4); }              \
+        else if ((H) == 2 && q__ == 2) { CALL(2, 2); }              \
+        else if ((H) == 2 && q__ == 4) { CALL(2, 4); }              \
+        else if ((H) == 2 && q__ == 8) { CALL(2, 8); }              \
+        else if ((H) == 4 && q__ == 4) { CALL(4, 4); }              \
+        else if ((H) == 4 && q__ == 8) { CALL(4, 8); }              \
+        else { set_error("GAT: unsupported heads=%d channels=%d", (H), (C)); return HICGAT_ERR_INVALID; } \
+    } while (0)
+
+}  // namespace
+}  // namespace hicgat
+
+using namespace hicgat;
+
+extern "C" int hicgat_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, int64_t n,
+                                   int64_t f, float* out, hicgat_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HICGAT_REQUIRE(rowptr && col && w && x && out && n > 0 && n < (1ll << 31), "hicgat_spmm_csr_f32: bad arguments");
+    HICGAT_REQUIRE(aligned16(x) && aligned16(out), "hicgat_spmm_csr_f32: x/out must be 16-byte aligned");
+    const unsigned grid = (unsigned)((n + kRowsPerCta - 1) / kRowsPerCta);
+    switch (f) {
+        case 128: spmm_kernel<1><<<grid, 256, 0, stream>>>(rowptr, col, w, x, (int)n, out); break;
+        case 256: spmm_kernel<2><<<grid, 256, 0, stream>>>(rowptr, col, w, x, (int)n, out); break;
+        case 512: spmm_kernel<4><<<grid, 256, 0, stream>>>(rowptr, col, w, x, (int)n, out); break;
+        case 1024: spmm_kernel<8><<<grid, 256, 0, stream>>>(rowptr, col, w, x, (int)n, out); break;
+        default: set_error("hicgat_spmm_csr_f32: feature width %lld not in {128,256,512,1024}", (long long)f); return HICGAT_ERR_INVALID;
+    }
+    HICGAT_CHECK_LAUNCH("spmm_kernel");
+    return HICGAT_OK;
+}
+
+extern "C" int hicgat_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n, int heads, int channels, const float* xl,
+                              const float* att_l, const float* att_r, const float* bias, float slope, float* a_src,
+                              float* a_dst, float* alpha, float* out, hicgat_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HICGAT_REQUIRE(rowptr && col && xl && att_l && att_r && bias && a_src && a_dst && alpha && out, "hicgat_gat_fwd: null pointer");
+    HICGAT_REQUIRE(n > 0 && n < (1ll << 31), "hicgat_gat_fwd: bad n");
+    HICGAT_REQUIRE(supported(heads, channels), "hicgat_gat_fwd: unsupported heads=%d channels=%d", heads, channels);
+    HICGAT_REQUIRE(aligned16(xl) && aligned16(out) && aligned16(att_l) && aligned16(att_r) && aligned16(bias), "hicgat_gat_fwd: 16-byte alignment required");
+    const unsigned grid = (unsigned)((n + kRowsPerCta - 1) / kRowsPerCta);
+#define CALL_LOGIT(H, Q) gat_logit_kernel<H, Q><<<grid, 256, 0, stream>>>(xl, att_l, att_r, (int)n, a_src, a_dst)
+    HICGAT_DISPATCH_HQ(heads, channels, CALL_LOGIT);
+#undef CALL_LOGIT
+    HICGAT_CHECK_LAUNCH("gat_logit_kernel");
+#define CALL_FWD(H, Q) gat_fwd_kernel<H, Q><<<grid, 256, 0, stream>>>(rowptr, col, xl, a_src, a_dst, bias, slope, (int)n, alpha, out)
+    HICGAT_DISPATCH_HQ(heads, channels, CALL_FWD);
+#undef CALL_FWD
+    HICGAT_CHECK_LAUNCH("gat_fwd_kernel");
+    return HICGAT_OK;
+}
+
+namespace {
+struct BwdLayout {
+    size_t off_dz, off_dsrc, off_ddst, off_part, off_counter, total;
+    int nchunks;
+};
+BwdLayout bwd_layout(int64_t n, int64_t nnz, int H, int C) {
+    BwdLayout L;
+    const size_t F = (size_t)H * C;
+    L.nchunks = (int)((n + kParamRows - 1) / kParamRows);
+    L.off_counter = 0;
+    L.off_dz = 256;
+    L.off_dsrc = L.off_dz + align_up(sizeof(float) * (size_t)nnz * H, 256);
+    L.off_ddst = L.off_dsrc + align_up(sizeof(float) * (size_t)n * H, 256);
+    L.off_part = L.off_ddst + align_up(sizeof(float) * (size_t)n * H, 256);
+    L.total = L.off_part + sizeof(float) * 3 * F * (size_t)L.nchunks;
+    return L;
+}
+}  // namespace
+
+extern "C" size_t hicgat_gat_bwd_workspace_bytes(int64_t n, int64_t nnz, int heads, int channels) {
+    if (n <= 0 || nnz < 0 || !supported(heads, channels)) return 0;
+    return bwd_layout(n, nnz, heads, channels).total;
+}
+
+extern "C" int hicgat_gat_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t nnz, int heads,
+                              int channels, const float* xl, const float* att_l, const float* att_r, float slope,
+                              const float* a_src, const float* a_dst, const float* alpha, const float* gout, float* dxl,
+                              float* datt_l, float* datt_r, float* dbias, void* workspace, size_t workspace_bytes,
+                              hicgat_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HICGAT_REQUIRE(rowptr && col && perm && xl && att_l && att_r && a_src && a_dst && alpha && gout && dxl && datt_l && datt_r && dbias && workspace,
+                   "hicgat_gat_bwd: null pointer");
+    HICGAT_REQUIRE(n > 0 && n < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "hicgat_gat_bwd: bad n/nnz");
+    HICGAT_REQUIRE(supported(heads, channels), "hicgat_gat_bwd: unsupported heads=%d channels=%d", heads, channels);
+    HICGAT_REQUIRE(aligned16(xl) && aligned16(gout) && aligned16(dxl) && aligned16(att_l) && aligned16(att_r), "hicgat_gat_bwd: 16-byte alignment required");
+    const BwdLayout L = bwd_layout(n, nnz, heads, channels);
+    if (workspace_bytes < L.total) {
+        set_error("hicgat_gat_bwd: workspace %zu < required %zu", workspace_bytes, L.total);
+        return HICGAT_ERR_WORKSPACE;
+    }
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    unsigned* counter = reinterpret_cast<unsigned*>(ws + L.off_counter);
+    float* dz = reinterpret_cast<float*>(ws + L.off_dz);
+    float* dsrc = reinterpret_cast<float*>(ws + L.off_dsrc);
+    float* ddst = reinterpret_cast<float*>(ws + L.off_ddst);
+    float* part = reinterpret_cast<float*>(ws + L.off_part);
+    HICGAT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
+    const unsigned grid = (unsigned)((n + kRowsPerCta - 1) / kRowsPerCta);
+#define CALL_EDGE(H, Q) gat_bwd_edge_kernel<H, Q><<<grid, 256, 0, stream>>>(rowptr, col, xl, a_src, a_dst, alpha, gout, slope, (int)n, dz, ddst)
+    HICGAT_DISPATCH_HQ(heads, channels, CALL_EDGE);
+#undef CALL_EDGE
+    HICGAT_CHECK_LAUNCH("gat_bwd_edge_kernel");
+#define CALL_NODE(H, Q) gat_bwd_node_kernel<H, Q><<<grid, 256, 0, stream>>>(rowptr, col, perm, alpha, dz, gout, att_l, att_r, ddst, (int)n, dsrc, dxl)
+    HICGAT_DISPATCH_HQ(heads, channels, CALL_NODE);
+#undef CALL_NODE
+    HICGAT_CHECK_LAUNCH("gat_bwd_node_kernel");
+    gat_bwd_param_kernel<<<L.nchunks, 256, 0, stream>>>(xl, gout, dsrc, ddst, (int)n, heads, channels, part, counter, datt_l, datt_r, dbias);
+    HICGAT_CHECK_LAUNCH("gat_bwd_param_kernel");
+    return HICGAT_OK;
+}

@@ -1,0 +1,83 @@
+"""The live networks of the reference with the same class names, zero-arg constructors,
+attribute names and ``state_dict`` keys:
+
+* ``Net``                                   -- models.py:14-55   (SAGEConv "HiC-GNN" net)
+* ``GATNetSelectiveResidualsUpdated``       -- models.py:614-691 ("the GAT net")
+* ``GATNetHeadsChanged3LayersLeakyReLUv2``  -- models.py:1010-1047
+
+``forward(x, edge_index[, edge_weight]) -> [N,N]`` and ``get_model(...) -> [N,3]`` are kept.
+``forward`` materialises the N x N distance matrix only for API parity; the training step
+uses ``get_model`` + ``hic_gnn_b200.pairwise_loss`` and never builds it.
+"""
+from __future__ import annotations
+
+import torch.nn.functional as F
+from torch import nn
+from torch.nn import LayerNorm, Linear
+
+from .layers import GATConv, SAGEConv
+from .ops import pairdist
+
+
+class _CoordNet(nn.Module):
+    def coords(self, x, edge_index, edge_weight=None):
+        return self.get_model(x, edge_index, edge_weight)
+
+    def forward(self, x, edge_index, edge_weight=None):
+        return pairdist(self.get_model(x, edge_index, edge_weight))  # cdist(x, x, p=2)
+
+
+class Net(_CoordNet):
+    def __init__(self):
+        super().__init__()
+        self.conv = SAGEConv(512, 512)
+        self.densea = Linear(512, 256)
+        self.dense1 = Linear(256, 128)
+        self.dense2 = Linear(128, 64)
+        self.dense3 = Linear(64, 3)
+
+    def get_model(self, x, edge_index, edge_weight=None):  # models.py:44-55
+        x = self.conv(x, edge_index, edge_weight).relu()
+        x = self.densea(x).relu()
+        x = self.dense1(x).relu()
+        x = self.dense2(x).relu()
+        return self.dense3(x)
+
+
+class GATNetSelectiveResidualsUpdated(_CoordNet):
+    def __init__(self):
+        super().__init__()
+        self.conv = GATConv(512, 256, heads=2, concat=True)
+        self.densea = Linear(512, 256)
+        self.norm_a = LayerNorm(256)
+        self.align_densea = Linear(512, 256)
+        self.dense1 = Linear(256, 128)
+        self.norm1 = LayerNorm(128)
+        self.align_dense1 = Linear(256, 128)
+        self.dense2 = Linear(128, 64)
+        self.norm2 = LayerNorm(64)
+        self.dense3 = Linear(64, 3)
+
+    def get_model(self, x, edge_index, edge_weight=None):  # models.py:664-691
+        x = F.relu(self.conv(x, edge_index, edge_weight))
+        x_initial = self.align_densea(x)
+        x = F.relu(self.norm_a(self.densea(x))) + x_initial
+        x_initial = self.align_dense1(x)
+        x = F.relu(self.norm1(self.dense1(x))) + x_initial
+        x = F.relu(self.norm2(self.dense2(x)))
+        return self.dense3(x)
+
+
+class GATNetHeadsChanged3LayersLeakyReLUv2(_CoordNet):
+    def __init__(self):
+        super().__init__()
+        self.conv = GATConv(512, 256, heads=2, concat=True)
+        self.densea = Linear(512, 256)
+        self.dense1 = Linear(256, 64)
+        self.dense2 = Linear(64, 3)
+
+    def get_model(self, x, edge_index, edge_weight=None):  # models.py:1036-1047
+        x = F.leaky_relu(self.conv(x, edge_index, edge_weight))
+        x = F.leaky_relu(self.densea(x))
+        x = F.leaky_relu(self.dense1(x))
+        return self.dense2(x)

@@ -1,0 +1,311 @@
+"""Torch-facing wrappers of the C ABI (device memory, streams and autograd only).
+
+Every function requires CUDA tensors and enqueues on torch's current stream; none has a CPU
+path.  Reference call sites are cited on each wrapper.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as N
+
+_MODES = {
+    "mse": N.PAIR_GRAD_MSE,
+    "mse_moments": N.PAIR_GRAD_MSE | N.PAIR_MOMENTS,
+    "contrastive": N.PAIR_GRAD_L1 | N.PAIR_MOMENTS,
+    "moments": N.PAIR_MOMENTS,
+    "value": 0,
+}
+
+
+def _cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("hic_gnn_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------ target
+class WishTarget:
+    """f32 wish-distance row block ``rows [r0, r1) x n`` with a 16-byte-aligned pitch.
+
+    The layout the fused loss kernel streams (``truth.float()`` of HiC-GNN_main.py:127,
+    stored once instead of re-cast every iteration)."""
+
+    def __init__(self, data: torch.Tensor, n: int, r0: int, r1: int):
+        _cuda(data)
+        assert data.dtype == torch.float32 and data.dim() == 2 and data.stride(1) == 1
+        assert data.shape[0] == r1 - r0 and data.stride(0) % 4 == 0 and data.stride(0) >= n
+        self.data, self.n, self.r0, self.r1 = data, n, r0, r1
+
+    @property
+    def pitch(self) -> int:
+        return self.data.stride(0)
+
+    @staticmethod
+    def pitch_for(n: int) -> int:
+        return (n + 3) // 4 * 4
+
+    @classmethod
+    def empty(cls, n: int, r0: int = 0, r1: int | None = None, device="cuda"):
+        r1 = n if r1 is None else r1
+        buf = torch.zeros(max(r1 - r0, 1), cls.pitch_for(n), dtype=torch.float32, device=device)
+        return cls(buf[: r1 - r0], n, r0, r1)
+
+    @classmethod
+    def from_dense(cls, truth: torch.Tensor, r0: int = 0, r1: int | None = None):
+        """Copy rows [r0,r1) of an N x N (f32/f64) CUDA matrix into the padded layout."""
+        _cuda(truth)
+        n = truth.shape[0]
+        r1 = n if r1 is None else r1
+        out = cls.empty(n, r0, r1, truth.device)
+        out.data[:, :n].copy_(truth[r0:r1])
+        return out
+
+    def dense(self) -> torch.Tensor:
+        return self.data[:, : self.n]
+
+
+# ------------------------------------------------------------------------------ pair loss
+class _PairWorkspace:
+    _cache: dict = {}
+
+    @classmethod
+    def get(cls, device, n, r0, r1):
+        key = (device.index, n, r0, r1)
+        ws = cls._cache.get(key)
+        need = N.lib().hicgat_pairloss_workspace_bytes(n, r0, r1)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+            cls._cache[key] = ws
+        return ws
+
+
+def pairloss_raw(coords: torch.Tensor, target: WishTarget, mode: int, c_mse: float, c_l1: float, moments=None, grad=None):
+    """One launch of ``hicgat_pairloss_fwd_bwd``: returns ``(moments f64[8], grad f32[n,3])``."""
+    _cuda(coords, target.data)
+    if coords.dtype != torch.float32 or coords.shape != (target.n, 3):
+        raise RuntimeError(f"coords must be float32 [n,3] with n={target.n}, got {coords.dtype} {tuple(coords.shape)}")
+    coords = coords.contiguous()
+    n = target.n
+    if moments is None:
+        moments = torch.empty(N.PAIR_NMOM, dtype=torch.float64, device=coords.device)
+    if grad is None and (mode & 3):
+        grad = torch.empty(n, 3, dtype=torch.float32, device=coords.device)
+    ws = _PairWorkspace.get(coords.device, n, target.r0, target.r1)
+    rc = N.lib().hicgat_pairloss_fwd_bwd(
+        coords.data_ptr(), target.data.data_ptr(), target.pitch, n, target.r0, target.r1, mode, c_mse, c_l1,
+        moments.data_ptr(), _ptr(grad), ws.data_ptr(), ws.numel(), _stream(),
+    )
+    N.check(rc, "hicgat_pairloss_fwd_bwd")
+    return moments, grad
+
+
+def pearson_from_moments(m: torch.Tensor, npairs: float) -> torch.Tensor:
+    """Pearson r of (d, t) over i<j from raw f64 moments (scipy.stats.pearsonr's value,
+    HiC_GAT_generalize_directly.py:220)."""
+    sd, sdd, st, stt, sdt = m[2], m[3], m[4], m[5], m[6]
+    cov = sdt - sd * st / npairs
+    vd = sdd - sd * sd / npairs
+    vt = stt - st * st / npairs
+    return (cov / torch.sqrt(vd * vt)).clamp(-1.0, 1.0)
+
+
+class _PairLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords, target, mode_name, reducer):
+        n = target.n
+        npairs = n * (n - 1) / 2.0
+        mode = _MODES[mode_name]
+        c_mse, c_l1 = 4.0 / (float(n) * float(n)), 0.1 / max(npairs, 1.0)
+        if reducer is not None:  # row-sharded: local block + one packed all-reduce (sharding.py)
+            moments, grad = reducer(coords.detach())
+        else:
+            moments, grad = pairloss_raw(coords.detach(), target, mode, c_mse, c_l1)
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(moments)
+        if mode_name == "contrastive":
+            loss = 0.1 * moments[1] / npairs  # f64, like the reference (:131-134)
+        else:
+            loss = (moments[0] / (float(n) * float(n))).to(torch.float32)  # MSELoss over N x N
+        return loss, moments
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_moments):
+        (grad,) = ctx.saved_tensors
+        return grad * g_loss.to(grad.dtype), None, None, None
+
+
+def pairwise_loss(coords: torch.Tensor, target: WishTarget, mode: str = "mse", reducer=None):
+    """Fused replacement of ``cdist`` + loss + backward.  Returns ``(loss, moments)``.
+
+    mode ``"mse"``          MSELoss(cdist(coords), truth)            HiC-GNN_main.py:126-127
+         ``"mse_moments"``  same + Pearson/L1 moments in one pass    HiC_GAT_generalize_directly.py:206-225
+         ``"contrastive"``  0.1*mean_{i<j}|t-d| (f64)                train_and_test_same_res_GAT_node2vec.py:131-134
+    """
+    if mode not in ("mse", "mse_moments", "contrastive"):
+        raise ValueError(mode)
+    return _PairLossFn.apply(coords, target, mode, reducer)
+
+
+def sharded_reducer(target: WishTarget, mode: str, group=None):
+    """``reducer`` for :func:`pairwise_loss` when ``target`` is this rank's row block."""
+    from . import sharding
+
+    n = target.n
+    npairs = n * (n - 1) / 2.0
+    fn = sharding.cuda_local_fn(target, _MODES[mode], 4.0 / (float(n) * float(n)), 0.1 / max(npairs, 1.0))
+    return sharding.ShardedPairLoss(n, fn, target.data.device, group)
+
+
+def pair_moments(coords: torch.Tensor, target: WishTarget) -> torch.Tensor:
+    """Moments only (no gradient): evaluation-time Pearson / MSE / dRMSD inputs."""
+    m, _ = pairloss_raw(coords.detach(), target, _MODES["moments"], 0.0, 0.0)
+    return m
+
+
+class _PairDistFn(torch.autograd.Function):
+    """Materialised ``torch.cdist(x, x, p=2)`` (models.py:39) for API parity of forward()."""
+
+    @staticmethod
+    def forward(ctx, coords):
+        _cuda(coords)
+        c = coords.detach().contiguous().float()
+        n = c.shape[0]
+        out = torch.empty(n, n, dtype=torch.float32, device=c.device)
+        N.check(N.lib().hicgat_pairdist_fwd(c.data_ptr(), n, out.data_ptr(), n, _stream()), "hicgat_pairdist_fwd")
+        ctx.save_for_backward(c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (c,) = ctx.saved_tensors
+        n = c.shape[0]
+        g = g.contiguous().float()
+        gc = torch.empty_like(c)
+        N.check(N.lib().hicgat_pairdist_bwd(c.data_ptr(), n, g.data_ptr(), n, gc.data_ptr(), _stream()), "hicgat_pairdist_bwd")
+        return gc
+
+
+def pairdist(coords: torch.Tensor) -> torch.Tensor:
+    return _PairDistFn.apply(coords)
+
+
+# ------------------------------------------------------------------------------ builders
+def cont2dist(adj: torch.Tensor, factor: float, want_f64: bool = True, want_f32: bool = False, r0: int = 0, r1: int | None = None, max_reduce=None):
+    """``utils.cont2dist`` (utils.py:75-80) on the GPU.  ``adj``: f64 CUDA rows [r0,r1) x n.
+
+    Returns ``(f64 matrix or None, WishTarget or None)``.  ``max_reduce`` (sharded builds) is
+    called on the device scalar between the two passes (an all-reduce(max))."""
+    _cuda(adj)
+    if adj.dtype != torch.float64 or adj.dim() != 2 or adj.stride(1) != 1:
+        raise RuntimeError("cont2dist expects a row-major float64 CUDA matrix")
+    n = adj.shape[1]
+    r1 = n if r1 is None else r1
+    if adj.shape[0] != r1 - r0:
+        raise RuntimeError("adj must hold exactly rows [r0, r1)")
+    lib = N.lib()
+    mx = torch.empty(1, dtype=torch.float64, device=adj.device)
+    ws = torch.empty(lib.hicgat_cont2dist_workspace_bytes(n, r0, r1), dtype=torch.uint8, device=adj.device)
+    N.check(lib.hicgat_cont2dist_max_f64(adj.data_ptr(), adj.stride(0), n, r0, r1, float(factor), mx.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "hicgat_cont2dist_max_f64")
+    if max_reduce is not None:
+        max_reduce(mx)
+    o64 = torch.empty(r1 - r0, n, dtype=torch.float64, device=adj.device) if want_f64 else None
+    tgt = WishTarget.empty(n, r0, r1, adj.device) if want_f32 else None
+    N.check(
+        lib.hicgat_cont2dist_apply_f64(
+            adj.data_ptr(), adj.stride(0), n, r0, r1, float(factor), mx.data_ptr(),
+            _ptr(o64), n, _ptr(tgt.data) if tgt is not None else None, tgt.pitch if tgt is not None else 0, _stream(),
+        ),
+        "hicgat_cont2dist_apply_f64",
+    )
+    return o64, tgt
+
+
+def csr_from_dense(adj: torch.Tensor, with_self_loops: bool = False):
+    """Graph half of ``utils.load_input`` (utils.py:33-71) on the GPU: returns
+    ``(rowptr int64[n+1], col int64[nnz], value f32[nnz])``, bit-exact with the reference."""
+    _cuda(adj)
+    if adj.dtype != torch.float64 or adj.dim() != 2 or adj.shape[0] != adj.shape[1] or adj.stride(1) != 1:
+        raise RuntimeError("csr_from_dense expects a square row-major float64 CUDA matrix")
+    n = adj.shape[0]
+    lib = N.lib()
+    counts = torch.empty(n, dtype=torch.int64, device=adj.device)
+    rowptr = torch.empty(n + 1, dtype=torch.int64, device=adj.device)
+    s = _stream()
+    N.check(lib.hicgat_csr_count_f64(adj.data_ptr(), adj.stride(0), n, int(with_self_loops), counts.data_ptr(), s), "hicgat_csr_count_f64")
+    N.check(lib.hicgat_csr_scan_i64(counts.data_ptr(), n, rowptr.data_ptr(), s), "hicgat_csr_scan_i64")
+    nnz = int(rowptr[-1].item())  # one host sync, at build time only
+    col = torch.empty(nnz, dtype=torch.int64, device=adj.device)
+    val = torch.empty(nnz, dtype=torch.float32, device=adj.device)
+    if nnz == 0:
+        return rowptr, col, val
+    N.check(lib.hicgat_csr_fill_f64(adj.data_ptr(), adj.stride(0), n, int(with_self_loops), rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), s), "hicgat_csr_fill_f64")
+    return rowptr, col, val
+
+
+# ------------------------------------------------------------------------------ host-buffer entry
+class HostPairLoss:
+    """Pairwise loss for a target that lives in (pinned) HOST memory: the row blocks are
+    streamed host->device through two staging buffers while the fused kernel consumes the
+    previous block (copy stream / compute stream, events), partial moments and gradients are
+    summed on the device and read back once.  This is the end-to-end path ``bench.py`` times
+    (``e2e``): PCIe-bound by construction; a training loop keeps the target resident instead.
+    """
+
+    def __init__(self, n: int, r0: int = 0, r1: int | None = None, block_rows: int = 2048, device="cuda"):
+        self.n, self.r0, self.r1 = n, r0, n if r1 is None else r1
+        self.block_rows = block_rows
+        self.device = torch.device(device)
+        self.pitch = WishTarget.pitch_for(n)
+        self.stage = [torch.empty(block_rows, self.pitch, dtype=torch.float32, device=device) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        self.coords_dev = torch.empty(n, 3, dtype=torch.float32, device=device)
+        self.packed = torch.zeros(N.PAIR_NMOM + 3 * n, dtype=torch.float64, device=device)
+        self.acc = torch.zeros_like(self.packed)
+        self.out_host = torch.empty(N.PAIR_NMOM + 3 * n, dtype=torch.float64).pin_memory()
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def __call__(self, coords_host: torch.Tensor, target_host: torch.Tensor, mode: int, c_mse: float, c_l1: float):
+        """``coords_host`` f32 [n,3] (pinned), ``target_host`` f32 [r1-r0, pitch] (pinned)."""
+        assert not coords_host.is_cuda and not target_host.is_cuda
+        assert target_host.shape == (self.r1 - self.r0, self.pitch) and target_host.dtype == torch.float32
+        main = torch.cuda.current_stream()
+        self.coords_dev.copy_(coords_host, non_blocking=True)
+        self.acc.zero_()
+        self.h2d_bytes = coords_host.numel() * 4
+        lib = N.lib()
+        nblk = (self.r1 - self.r0 + self.block_rows - 1) // self.block_rows
+        for b in range(nblk):
+            s = b & 1
+            lo = b * self.block_rows
+            hi = min(lo + self.block_rows, self.r1 - self.r0)
+            with torch.cuda.stream(self.copy_stream):
+                if b >= 2:
+                    self.copy_stream.wait_event(self.free[s])
+                self.stage[s][: hi - lo].copy_(target_host[lo:hi], non_blocking=True)
+                self.ready[s].record(self.copy_stream)
+            self.h2d_bytes += (hi - lo) * self.pitch * 4
+            main.wait_event(self.ready[s])
+            ws = _PairWorkspace.get(self.device, self.n, self.r0 + lo, self.r0 + hi)
+            rc = lib.hicgat_pairloss_fwd_bwd_packed(
+                self.coords_dev.data_ptr(), self.stage[s].data_ptr(), self.pitch, self.n, self.r0 + lo, self.r0 + hi,
+                mode, c_mse, c_l1, self.packed.data_ptr(), ws.data_ptr(), ws.numel(), main.cuda_stream,
+            )
+            N.check(rc, "hicgat_pairloss_fwd_bwd_packed")
+            self.acc.add_(self.packed)
+            self.free[s].record(main)
+        self.out_host.copy_(self.acc, non_blocking=True)
+        self.d2h_bytes = self.out_host.numel() * 8
+        main.synchronize()
+        return self.out_host[: N.PAIR_NMOM], self.out_host[N.PAIR_NMOM:].view(self.n, 3)

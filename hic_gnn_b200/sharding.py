@@ -1,0 +1,76 @@
+"""Row-block sharding of the pairwise loss across the GPUs of one box.
+
+Rank r owns target rows ``[r*ceil(N/G), (r+1)*ceil(N/G))`` x all N columns.  The GNN is
+replicated, so every rank already holds identical N x 3 coordinates; per step each rank runs
+the fused kernel on its block and ONE all-reduce(sum) of the packed f64 buffer
+``[8 moments | 3N gradient]`` (<= 1.2 MB at 50k loci: latency-bound) combines them.
+Host-side logic is backend-agnostic: the gloo tests run it on CPU tensors with a stand-in
+for the kernel.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+
+
+def row_block(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous row range of ``rank``; trailing ranks may be short or empty."""
+    per = (n + world - 1) // world
+    r0 = min(rank * per, n)
+    return r0, min(r0 + per, n)
+
+
+def all_blocks(n: int, world: int) -> list[tuple[int, int]]:
+    return [row_block(n, r, world) for r in range(world)]
+
+
+def unpack(packed: torch.Tensor, n: int):
+    """packed f64[8+3n] -> (moments f64[8], grad f32[n,3])."""
+    return packed[: N.PAIR_NMOM], packed[N.PAIR_NMOM:].view(n, 3).to(torch.float32)
+
+
+def allreduce_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """The single per-step collective.  No-op without an initialised process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed
+
+
+def allreduce_max_(x: torch.Tensor, group=None) -> torch.Tensor:
+    """Global max for the sharded wish-distance build (between cont2dist's two passes)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(x, op=dist.ReduceOp.MAX, group=group)
+    return x
+
+
+class ShardedPairLoss:
+    """Callable ``(coords) -> (moments, grad)`` over this rank's row block + one all-reduce.
+    ``local_fn(coords, packed)`` fills the packed buffer for the local block (the CUDA kernel
+    in production; tests inject a CPU stand-in)."""
+
+    def __init__(self, n: int, local_fn, device, group=None):
+        self.n, self.local_fn, self.group = n, local_fn, group
+        self.packed = torch.zeros(N.PAIR_NMOM + 3 * n, dtype=torch.float64, device=device)
+
+    def __call__(self, coords: torch.Tensor):
+        self.local_fn(coords, self.packed)
+        allreduce_packed(self.packed, self.group)
+        return unpack(self.packed, self.n)
+
+
+def cuda_local_fn(target, mode: int, c_mse: float, c_l1: float):
+    """The production ``local_fn``: hicgat_pairloss_fwd_bwd_packed on this rank's WishTarget."""
+    from .ops import _PairWorkspace, _cuda, _stream
+
+    def fn(coords: torch.Tensor, packed: torch.Tensor):
+        _cuda(coords, packed)
+        ws = _PairWorkspace.get(coords.device, target.n, target.r0, target.r1)
+        rc = N.lib().hicgat_pairloss_fwd_bwd_packed(
+            coords.contiguous().data_ptr(), target.data.data_ptr(), target.pitch, target.n, target.r0, target.r1,
+            mode, c_mse, c_l1, packed.data_ptr(), ws.data_ptr(), ws.numel(), _stream(),
+        )
+        N.check(rc, "hicgat_pairloss_fwd_bwd_packed")
+
+    return fn

@@ -1,0 +1,182 @@
+/*
+ * hicgat.h -- C ABI of libhicgat_sm100.so: the B200 (sm_100a) kernels behind the
+ * HiC-GNN / GAT-HiC training hot path.
+ *
+ * The reference (beyzoskaya/HiC-GNN) is pure Python and has no FFI of its own; each entry
+ * point below names the reference Python call (file:line under /root/reference) whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add to call it.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the callee never allocates, frees or synchronises: outputs and workspaces are caller
+ *     owned, work is enqueued on `stream` (a cudaStream_t; 0 = legacy default stream), so
+ *     every call is CUDA-graph capturable;
+ *   - return value 0 = success, negative = error (see hicgat_last_error());
+ *   - matrices are row-major; `pitch`/`ld` arguments are in ELEMENTS, and rows handed to the
+ *     128-bit loaders must start 16-byte aligned (pitch % 4 == 0 for f32, % 2 for f64).
+ */
+#ifndef HICGAT_H_
+#define HICGAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* hicgat_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define HICGAT_API __attribute__((visibility("default")))
+#else
+#define HICGAT_API
+#endif
+
+#define HICGAT_OK 0
+#define HICGAT_ERR_INVALID (-1)   /* bad argument (null pointer, misaligned, negative size) */
+#define HICGAT_ERR_CUDA (-2)      /* a CUDA runtime call / launch failed */
+#define HICGAT_ERR_WORKSPACE (-3) /* workspace too small */
+
+HICGAT_API int hicgat_version(void);
+/* Thread-local, human-readable description of the last non-zero return on this thread. */
+HICGAT_API const char* hicgat_last_error(void);
+/* Number of kernel launches this library has enqueued since load (bench `gpu_launches`). */
+HICGAT_API uint64_t hicgat_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * (2) Fused pairwise-distance loss, forward + backward in one pass over the target.
+ *
+ * Replaces, per training iteration:  torch.cdist(coords, coords)            models.py:39,661,1033
+ *                                    MSELoss()(out.float(), truth.float())  HiC-GNN_main.py:127
+ *                                    triu_indices gathers + pearsonr inputs HiC_GAT_generalize_directly.py:210-220
+ *                                    0.1*mean|t-d| over i<j                 train_and_test_same_res_GAT_node2vec.py:131-134
+ *                                    and their autograd backward (ATen _euclidean_dist_backward).
+ *
+ * coords  [n,3] f32.  target: f32 row block, rows [r0,r1) of the n x n wish-distance matrix,
+ * `target` points at row r0, row pitch `pitch` elements (>= n, multiple of 4).  The target is
+ * assumed symmetric with a zero diagonal (cont2dist of a symmetric map, utils.py:75-80):
+ * column-side accumulation then yields COMPLETE gradients without atomics.
+ *
+ * mode bits select what is accumulated (S_ee is always produced):
+ *   HICGAT_PAIR_GRAD_MSE  grad += c_mse * sum_i (d-t)/d * (x_j - x_i)      [c_mse = 4/n^2 for MSELoss]
+ *   HICGAT_PAIR_GRAD_L1   grad += c_l1  * sum_i sign(d-t)/d * (x_j - x_i)  [c_l1 = 0.1/P for the contrastive loss]
+ *   HICGAT_PAIR_MOMENTS   strict-upper-triangle statistics for Pearson / L1 / dRMSD
+ *
+ * moments (f64[HICGAT_PAIR_NMOM], this rank's rows only; sum across ranks when sharded):
+ *   [0] sum_{i in [r0,r1), all j} (d-t)^2          [1] sum_{i<j} |d-t|
+ *   [2] sum_{i<j} d    [3] sum_{i<j} d^2           [4] sum_{i<j} t    [5] sum_{i<j} t^2
+ *   [6] sum_{i<j} d*t  [7] sum_{i<j} (d-t)^2
+ * grad [n,3] f32: this rank's contribution to dLoss/dcoords for ALL n loci (all-reduce when
+ * sharded).  Results are bit-reproducible run to run (fixed-order reductions, no float atomics).
+ * ---------------------------------------------------------------------------------- */
+#define HICGAT_PAIR_GRAD_MSE 1u
+#define HICGAT_PAIR_GRAD_L1 2u
+#define HICGAT_PAIR_MOMENTS 4u
+#define HICGAT_PAIR_NMOM 8
+
+HICGAT_API size_t hicgat_pairloss_workspace_bytes(int64_t n, int64_t r0, int64_t r1);
+HICGAT_API int hicgat_pairloss_fwd_bwd(const float* coords, const float* target, int64_t pitch, int64_t n,
+                            int64_t r0, int64_t r1, uint32_t mode, float c_mse, float c_l1,
+                            double* moments, float* grad, void* workspace, size_t workspace_bytes,
+                            hicgat_stream_t stream);
+/* Row-sharded variant: one f64 buffer packed[HICGAT_PAIR_NMOM + 3n] = [moments | grad] so that
+ * a single all-reduce(sum) over NVLink combines the ranks (grad values are the f32 results,
+ * widened). */
+HICGAT_API int hicgat_pairloss_fwd_bwd_packed(const float* coords, const float* target, int64_t pitch,
+                                   int64_t n, int64_t r0, int64_t r1, uint32_t mode, float c_mse,
+                                   float c_l1, double* packed, void* workspace,
+                                   size_t workspace_bytes, hicgat_stream_t stream);
+/* Tuning hook (bench/tests): rows per CTA row-chunk and kernel variant; 0 = library default. */
+HICGAT_API int hicgat_pairloss_set_tuning(int rows_per_cta, int variant);
+
+/* Materialising variant kept for API parity of model.forward() (returns the N x N matrix,
+ * models.py:39): dist[i,j] = |x_i - x_j|, and its backward
+ * grad_coords[i] = sum_j (G[i,j] + G[j,i]) (x_i - x_j)/d_ij  (ATen _euclidean_dist_backward). */
+HICGAT_API int hicgat_pairdist_fwd(const float* coords, int64_t n, float* dist, int64_t pitch,
+                        hicgat_stream_t stream);
+HICGAT_API int hicgat_pairdist_bwd(const float* coords, int64_t n, const float* grad_dist, int64_t pitch,
+                        float* grad_coords, hicgat_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Wish-distance builder.  Replaces utils.cont2dist (utils.py:75-80) plus the per-iteration
+ * truth.float() cast (HiC-GNN_main.py:127).
+ *   pass 1: max over finite off-diagonal (1/a)^factor     -> max_out (f64 scalar, device)
+ *   pass 2: out = diag ? 0 : (a==0 ? 1 : (1/a)^factor/max) -> f64 (parity) and/or f32 (training)
+ * `adj` f64 rows [r0,r1) of the n x n contact matrix (pointer at row r0).  Either output
+ * pointer may be NULL.  When sharded, all-reduce(max) `max_out` between the passes.
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API int hicgat_cont2dist_max_f64(const double* adj, int64_t ld, int64_t n, int64_t r0, int64_t r1,
+                             double factor, double* max_out, void* workspace,
+                             size_t workspace_bytes, hicgat_stream_t stream);
+HICGAT_API int hicgat_cont2dist_apply_f64(const double* adj, int64_t ld, int64_t n, int64_t r0, int64_t r1,
+                               double factor, const double* max_in, double* out_f64,
+                               int64_t ld_f64, float* out_f32, int64_t pitch_f32,
+                               hicgat_stream_t stream);
+HICGAT_API size_t hicgat_cont2dist_workspace_bytes(int64_t n, int64_t r0, int64_t r1);
+
+/* ------------------------------------------------------------------------------------
+ * (1a) CSR graph build.  Replaces the graph half of utils.load_input (utils.py:33-71:
+ * networkx edge walk, SparseTensor sort, to_symmetric) -- bit-exact:
+ *   edge {i,j}, i != j, exists iff A[i,j] != 0 or A[j,i] != 0;
+ *   value = (float)(A[max,min] != 0 ? A[max,min] : A[min,max]); columns ascending.
+ * `with_self_loops` != 0 additionally inserts (i,i) with value 1 at its sorted position
+ * (torch-sparse set_diag, which GATConv applies on every forward).
+ *   count: rowcount[i] = entries of row i (int64[n])
+ *   scan : rowptr = exclusive scan (int64[n+1]), any n
+ *   fill : col int64[nnz], val f32[nnz]
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API int hicgat_csr_count_f64(const double* adj, int64_t ld, int64_t n, int with_self_loops,
+                         int64_t* rowcount, hicgat_stream_t stream);
+HICGAT_API int hicgat_csr_scan_i64(const int64_t* rowcount, int64_t n, int64_t* rowptr,
+                        hicgat_stream_t stream);
+HICGAT_API int hicgat_csr_fill_f64(const double* adj, int64_t ld, int64_t n, int with_self_loops,
+                        const int64_t* rowptr, int64_t* col, float* val, hicgat_stream_t stream);
+/* int32 copy of the column indices for the conv kernels + per-row inverse weight sums
+ * (SAGEConv.adjust_weights, layers.py:41-54: norm_val = val / colsum[row]). */
+HICGAT_API int hicgat_csr_pack_i32(const int64_t* rowptr, const int64_t* col, int64_t n, int64_t nnz,
+                        int32_t* rowptr32, int32_t* col32, hicgat_stream_t stream);
+/* torch-sparse set_diag on a diagonal-free pattern: out has nnz + n entries (GATConv self loops). */
+HICGAT_API int hicgat_csr_add_self_loops_i32(const int32_t* rowptr, const int32_t* col, int64_t n,
+                                  int32_t* out_rowptr, int32_t* out_col, hicgat_stream_t stream);
+HICGAT_API int hicgat_sage_norm_values(const int32_t* rowptr, const int32_t* col, const float* val,
+                            int64_t n, float* colsum, float* norm_val, hicgat_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (1b) SAGEConv aggregation (layers.py:75-79): out[i,:] = sum_k w[k] * x[col[k],:] over row i
+ * in CSR order; backward dx[j,:] = sum_{i: j in row i} w_ij * g[i,:] -- computed with the
+ * transposed weights `w_t` (pattern is symmetric, so rowptr/col are shared).
+ * f = feature width (multiple of 4).  One warp per row, float4 gathers.
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API int hicgat_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* w,
+                        const float* x, int64_t n, int64_t f, float* out,
+                        hicgat_stream_t stream);
+/* perm[k] = position of the transposed entry (col[k], row(k)) ; w_t = w[perm]. */
+HICGAT_API int hicgat_csr_transpose_perm(const int32_t* rowptr, const int32_t* col, int64_t n,
+                              int32_t* perm, hicgat_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (1c) GATConv message passing (torch-geometric 1.7.2 GATConv, ctor sites models.py:619,1013;
+ * semantics in SURVEY.md Appendix A.3).  `xl` [n, H*C] = lin_l(x) (cuBLAS, outside);
+ * CSR pattern includes self loops.  H in {1,2,4}, C multiple of 128/H... see gat.cu.
+ *   fwd : a_src/a_dst [n,H] (logit halves), alpha [nnz,H] (saved attention), out [n,H*C]
+ *         out = softmax_row(leaky_relu(a_src[j] + a_dst[i], slope)) @ xl  + bias
+ *   bwd : given g = dL/dout: dxl [n,H*C], datt_l/datt_r [H*C] (+=), dbias [H*C]
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API int hicgat_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n, int heads, int channels,
+                   const float* xl, const float* att_l, const float* att_r, const float* bias,
+                   float slope, float* a_src, float* a_dst, float* alpha, float* out,
+                   hicgat_stream_t stream);
+HICGAT_API size_t hicgat_gat_bwd_workspace_bytes(int64_t n, int64_t nnz, int heads, int channels);
+HICGAT_API int hicgat_gat_bwd(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n,
+                   int64_t nnz, int heads, int channels, const float* xl, const float* att_l,
+                   const float* att_r, float slope, const float* a_src, const float* a_dst,
+                   const float* alpha, const float* gout, float* dxl, float* datt_l,
+                   float* datt_r, float* dbias, void* workspace, size_t workspace_bytes,
+                   hicgat_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HICGAT_H_ */

@@ -1,0 +1,178 @@
+"""GPU parity of the fused pairwise-distance loss (called through the C ABI) against the
+oracle's torch.cdist + MSELoss / L1 / scipy glue.  Tolerance: 1e-5 relative on loss values and
+gradients (north_star), written next to each assert."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import random_coords, rel_err, small_map, wish_from_map
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _oracle_mse(coords, truth):
+    from oracle import loss as oloss
+
+    c = coords.clone().requires_grad_(True)
+    l = oloss.mse_loss(c, truth)
+    (g,) = torch.autograd.grad(l, c)
+    return l.detach(), g
+
+
+def _oracle_contrastive(coords, truth):
+    from oracle import loss as oloss
+
+    c = coords.clone().requires_grad_(True)
+    l = oloss.contrastive_loss(c, truth)
+    (g,) = torch.autograd.grad(l, c)
+    return l.detach(), g
+
+
+def _gpu_loss(coords, truth, mode):
+    import hic_gnn_b200 as hg
+
+    tgt = hg.WishTarget.from_dense(truth.cuda())
+    c = coords.cuda().requires_grad_(True)
+    loss, moments = hg.pairwise_loss(c, tgt, mode)
+    (g,) = torch.autograd.grad(loss, c)
+    return loss.detach().cpu(), g.cpu(), moments.cpu()
+
+
+@pytest.mark.parametrize("tag", ["1mb", "500kb"])
+def test_mse_on_reference_maps(golden, tag):
+    g, _ = golden
+    truth = wish_from_map(torch.tensor(g[f"{tag}_kr_oracle"]), 1.0)
+    coords = random_coords(truth.shape[0], seed=1)
+    want_l, want_g = _oracle_mse(coords, truth)
+    got_l, got_g, _ = _gpu_loss(coords, truth, "mse")
+    assert got_l.dtype == torch.float32
+    assert abs(float(got_l) - float(want_l)) / float(want_l) < TOL
+    assert rel_err(got_g, want_g) < TOL
+
+
+@pytest.mark.parametrize("n,density", [(1, 1.0), (2, 1.0), (3, 1.0), (31, 0.9), (127, 0.5), (128, 0.5), (129, 0.5), (300, 0.95), (1000, 0.3), (2493, 0.95)])
+def test_mse_random_maps(n, density):
+    truth = wish_from_map(small_map(n, density, seed=n), 1.0) if n > 3 else torch.rand(n, n, dtype=torch.float64)
+    truth = (truth + truth.t()) / 2
+    truth.fill_diagonal_(0)
+    coords = random_coords(n, seed=n + 1)
+    want_l, want_g = _oracle_mse(coords, truth)
+    got_l, got_g, _ = _gpu_loss(coords, truth, "mse")
+    assert abs(float(got_l) - float(want_l)) <= TOL * max(float(want_l), 1e-12)
+    if n > 1:
+        assert rel_err(got_g, want_g) < TOL
+
+
+@pytest.mark.parametrize("n", [58, 300, 1000])
+def test_moments_match_scipy_and_contrastive(n):
+    from scipy.stats import pearsonr
+
+    from hic_gnn_b200.ops import pearson_from_moments
+    from oracle import loss as oloss
+
+    truth = wish_from_map(small_map(n, 0.6, seed=5), 1.0)
+    coords = random_coords(n, seed=2)
+    dist_truth, dist_out = oloss.triu_pairs(truth, coords)
+    want_r = pearsonr(dist_truth.numpy(), dist_out.numpy())[0]
+    got_l, got_g, m = _gpu_loss(coords, truth, "mse_moments")
+    npairs = n * (n - 1) / 2
+    assert abs(float(pearson_from_moments(m, npairs)) - want_r) < 1e-6
+    want_l, want_g = _oracle_mse(coords, truth)
+    assert abs(float(got_l) - float(want_l)) / float(want_l) < TOL and rel_err(got_g, want_g) < TOL
+    # raw moments
+    d, t = dist_out.double(), dist_truth.double()
+    for k, want in [(1, (d - t).abs().sum()), (2, d.sum()), (3, (d * d).sum()), (4, t.sum()), (5, (t * t).sum()), (6, (d * t).sum()), (7, ((d - t) ** 2).sum())]:
+        assert abs(float(m[k]) - float(want)) / float(want) < TOL, k
+    # contrastive mode: value (f64 like the reference) and gradient
+    want_l, want_g = _oracle_contrastive(coords, truth)
+    got_l, got_g, _ = _gpu_loss(coords, truth, "contrastive")
+    assert got_l.dtype == torch.float64
+    assert abs(float(got_l) - float(want_l)) / float(want_l) < TOL
+    assert rel_err(got_g, want_g) < TOL
+
+
+def test_row_sharded_blocks_sum_to_full_and_are_deterministic():
+    import hic_gnn_b200 as hg
+    from hic_gnn_b200 import ops
+
+    n = 777
+    truth = wish_from_map(small_map(n, 0.4, seed=8), 1.0).cuda()
+    coords = random_coords(n, seed=3).cuda()
+    full = hg.WishTarget.from_dense(truth)
+    mode = ops._MODES["mse_moments"]
+    m_full, g_full = ops.pairloss_raw(coords, full, mode, 4.0 / n**2, 0.0)
+    m_full2, g_full2 = ops.pairloss_raw(coords, full, mode, 4.0 / n**2, 0.0)
+    assert torch.equal(m_full, m_full2) and torch.equal(g_full, g_full2)  # bit-reproducible
+    m_sum = torch.zeros_like(m_full)
+    g_sum = torch.zeros_like(g_full)
+    for r0, r1 in [(0, 200), (200, 200), (200, 601), (601, 777)]:  # includes an empty block
+        blk = hg.WishTarget.from_dense(truth, r0, r1)
+        m, g = ops.pairloss_raw(coords, blk, mode, 4.0 / n**2, 0.0)
+        m_sum += m
+        g_sum += g
+    assert rel_err(m_sum, m_full) < 1e-12
+    assert rel_err(g_sum, g_full) < 1e-6
+
+
+def test_tuning_variants_agree():
+    import hic_gnn_b200 as hg
+    from hic_gnn_b200 import _native as N
+    from hic_gnn_b200 import ops
+
+    n = 1500
+    truth = wish_from_map(small_map(n, 0.5, seed=4), 1.0).cuda()
+    coords = random_coords(n, seed=5).cuda()
+    tgt = hg.WishTarget.from_dense(truth)
+    ref = None
+    try:
+        for rb in (0, 8, 64, 256, 1024):
+            assert N.lib().hicgat_pairloss_set_tuning(rb, 0) == 0
+            m, g = ops.pairloss_raw(coords, tgt, ops._MODES["mse_moments"], 4.0 / n**2, 0.0)
+            if ref is None:
+                ref = (m.clone(), g.clone())
+            assert rel_err(m, ref[0]) < 1e-7 and rel_err(g, ref[1]) < 1e-5
+    finally:
+        N.lib().hicgat_pairloss_set_tuning(0, 0)
+
+
+def test_pairdist_forward_backward_match_cdist():
+    import hic_gnn_b200 as hg
+
+    n = 200
+    coords = random_coords(n, seed=6)
+    w = torch.rand(n, n)
+    c = coords.clone().requires_grad_(True)
+    d_ref = torch.cdist(c, c, compute_mode="donot_use_mm_for_euclid_dist")
+    (g_ref,) = torch.autograd.grad((d_ref * w).sum(), c)
+    cg = coords.cuda().requires_grad_(True)
+    d = hg.pairdist(cg)
+    (g,) = torch.autograd.grad((d * w.cuda()).sum(), cg)
+    assert rel_err(d, d_ref) < 1e-6
+    assert rel_err(g, g_ref) < TOL
+
+
+@pytest.mark.parametrize("n", [9970])
+def test_full_size_closed_form_properties(n):
+    """Size-independent properties at a BASELINE.json size (10k loci, 1e8 pairs): with
+    target = pairwise distances of points y, coords = s*y gives MSE = (s-1)^2 mean(t^2),
+    gradient = 4(s-1)/n^2 * sum_j t_ij (y_i-y_j)/|y_i-y_j| ... checked through its closed-form
+    contraction <grad, y> = 2 s ... and Pearson r = 1; coords = y gives loss 0 and grad 0."""
+    import hic_gnn_b200 as hg
+    from hic_gnn_b200.ops import pearson_from_moments
+
+    y = random_coords(n, seed=11).cuda()
+    t = hg.pairdist(y)
+    tgt = hg.WishTarget.from_dense(t)
+    loss0, m0 = hg.pairwise_loss(y.clone().requires_grad_(True), tgt, "mse_moments")
+    assert float(loss0) < 1e-12
+    s = 1.25
+    c = (s * y).requires_grad_(True)
+    loss, m = hg.pairwise_loss(c, tgt, "mse_moments")
+    (g,) = torch.autograd.grad(loss, c)
+    mean_t2 = float((t.double() ** 2).mean())
+    assert abs(float(loss) - (s - 1) ** 2 * mean_t2) / ((s - 1) ** 2 * mean_t2) < TOL
+    # dL/ds = 2 (s-1) mean(t^2)  and  dL/ds = <grad, y>
+    assert abs(float((g.double() * y.double()).sum()) - 2 * (s - 1) * mean_t2) / (2 * (s - 1) * mean_t2) < TOL
+    assert abs(float(pearson_from_moments(m, n * (n - 1) / 2)) - 1.0) < 1e-6
+    assert abs(float(g.double().sum(0).abs().max())) < 1e-6  # translation invariance: sum_i grad_i = 0
