@@ -11,8 +11,9 @@
 namespace hicgat {
 namespace {
 
-// (1/a)^factor with ATen's pow special cases (exponent 1 -> copy, 0.5 -> sqrt, 2 -> square),
-// so factors 1 / 0.5 / 2 are bit-exact against torch's CPU result; generic factors use
+// (1/a)^factor with ATen's pow special cases (exponent 1 -> copy, 0.5 -> sqrt, 2 -> square).
+// Factors 1 and 2 are bit-exact against torch's CPU result; 0.5 is the correctly rounded IEEE
+// sqrt (torch's AVX-512 CPU sqrt is Sleef u05 and can be 1-2 ulp off it); generic factors use
 // CUDA's f64 pow (<= 2 ulp).
 __device__ __forceinline__ double inv_pow(double a, double factor, int fkind) {
     const double r = 1.0 / a;

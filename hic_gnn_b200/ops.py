@@ -260,8 +260,9 @@ class HostPairLoss:
     (``e2e``): PCIe-bound by construction; a training loop keeps the target resident instead.
     """
 
-    def __init__(self, n: int, r0: int = 0, r1: int | None = None, block_rows: int = 2048, device="cuda"):
+    def __init__(self, n: int, r0: int = 0, r1: int | None = None, block_rows: int = 2048, device="cuda", reduce=None):
         self.n, self.r0, self.r1 = n, r0, n if r1 is None else r1
+        self.reduce = reduce  # row-sharded runs: all-reduce of the packed device buffer before the read-back
         self.block_rows = block_rows
         self.device = torch.device(device)
         self.pitch = WishTarget.pitch_for(n)
@@ -272,7 +273,7 @@ class HostPairLoss:
         self.coords_dev = torch.empty(n, 3, dtype=torch.float32, device=device)
         self.packed = torch.zeros(N.PAIR_NMOM + 3 * n, dtype=torch.float64, device=device)
         self.acc = torch.zeros_like(self.packed)
-        self.out_host = torch.empty(N.PAIR_NMOM + 3 * n, dtype=torch.float64).pin_memory()
+        self.out_host = torch.empty(N.PAIR_NMOM + 3 * n, dtype=torch.float64, pin_memory=True)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -305,6 +306,8 @@ class HostPairLoss:
             N.check(rc, "hicgat_pairloss_fwd_bwd_packed")
             self.acc.add_(self.packed)
             self.free[s].record(main)
+        if self.reduce is not None:
+            self.reduce(self.acc)
         self.out_host.copy_(self.acc, non_blocking=True)
         self.d2h_bytes = self.out_host.numel() * 8
         main.synchronize()

@@ -66,3 +66,12 @@ def dscc(coords: torch.Tensor, truth: torch.Tensor) -> float:
 def pearson(coords: torch.Tensor, truth: torch.Tensor) -> float:
     dist_truth, dist_out = triu_pairs(truth, coords)
     return float(pearsonr(dist_truth.detach().numpy(), dist_out.detach().numpy())[0])
+
+
+def mse_loss_rows(coords: torch.Tensor, truth_rows: torch.Tensor, r0: int, r1: int) -> torch.Tensor:
+    """Rows ``[r0, r1)`` of :func:`mse_loss` (same ops: ``torch.cdist`` -> ``MSELoss``), for map
+    sizes whose N x N matrices the reference formulation cannot hold (it needs >125 GB of host
+    memory at 50k loci).  Summing ``value * (r1-r0)/N`` over a row partition gives ``mse_loss``;
+    ``bench.py`` times it on a bounded row sample as the CPU baseline."""
+    out = torch.cdist(coords[r0:r1], coords, p=2)
+    return MSELoss()(out.float(), truth_rows.float())

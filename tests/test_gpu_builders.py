@@ -89,14 +89,27 @@ def test_cont2dist_matches_reference_golden(golden, tag, factors):
     for f in factors:
         got = utils.cont2dist(y, f).cpu().numpy()
         want = g[f"{tag}_wish_{f}"]
-        if f in (0.5, 1.0):  # ATen special-cases these exponents: bit-exact
-            assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+        if f == 1.0:  # reciprocal, divide: IEEE on both sides -> bit-exact
+            exact = want
+        elif f == 0.5:
+            # ATen maps pow(., 0.5) to sqrt; its AVX-512 f64 sqrt (Sleef u05) is NOT correctly
+            # rounded (28 of 3364 elements of the 1 Mb golden are 1-2 ulp off IEEE sqrt), so the
+            # golden is matched to 2 ulp and the correctly rounded IEEE chain is matched bit for bit.
+            np.testing.assert_allclose(got, want, rtol=4.5e-16, atol=0)
+            with np.errstate(divide="ignore"):
+                s = np.sqrt(1.0 / g[f"{tag}_y"])
+            np.fill_diagonal(s, 0.0)
+            mx = s[np.isfinite(s)].max()
+            exact = np.where(np.isinf(s), mx, s) / mx
         else:  # generic pow: CUDA's f64 pow vs the host libm, <= a few ulp
             np.testing.assert_allclose(got, want, rtol=1e-14, atol=0)
+            exact = None
+        if exact is not None:
+            assert np.array_equal(got.view(np.uint64), exact.view(np.uint64))
         tgt = utils.wish_target(y, f)
         assert tgt.pitch % 4 == 0 and tgt.data.shape == (y.shape[0], tgt.pitch)
-        if f in (0.5, 1.0):
-            assert np.array_equal(tgt.dense().cpu().numpy(), want.astype(np.float32))
+        if exact is not None:
+            assert np.array_equal(tgt.dense().cpu().numpy(), exact.astype(np.float32))
         else:
             np.testing.assert_allclose(tgt.dense().cpu().numpy(), want.astype(np.float32), rtol=2e-7)
         assert float(tgt.data[:, y.shape[0]:].abs().sum()) == 0.0  # padding stays zero

@@ -44,18 +44,36 @@ def test_sage_aggregate_forward_backward(n, density):
         assert rel_err(a, b) < TOL
 
 
-@pytest.mark.parametrize("n,density,dense", [(58, 1.0, False), (114, 1.0, False), (300, 0.2, False), (700, 0.95, True)])
+def _gat_case(n, density, min_kink_gap=2e-6):
+    """Inputs + sharpened GATConv whose smallest |logit| over all edges stays away from the
+    LeakyReLU kink.  With ~1e6 edges some pre-activation z = a_src[j] + a_dst[i] falls within
+    f32 rounding (~1e-7) of 0 for about one seed in twenty; the slope (1 vs 0.2) of that edge is
+    then decided by summation order, in the oracle as much as in the kernel, and a single such
+    edge moves d/dx of its two rows by ~1e-4 relative.  Seeds are scanned deterministically."""
+    from oracle import conv as oconv
+    from oracle.graph import set_diag
+
+    for seed in range(2, 40):
+        _, x, odata, gdata = _setup(n, density, seed=seed)
+        torch.manual_seed(seed - 1)
+        oc = oconv.GATConv(512, 256, heads=2)
+        with torch.no_grad():
+            oc.bias.uniform_(-0.1, 0.1)
+            oc.att_l.mul_(3.0)  # sharper attention so the softmax is far from uniform
+            oc.att_r.mul_(3.0)
+            _, al, ar = oc._project(x)
+            g = set_diag(odata.edge_index)
+            gap = float((al[g.col] + ar[g.row]).abs().min())
+        if gap > min_kink_gap:
+            return x, odata, gdata, oc
+    raise AssertionError("no kink-safe seed found")
+
+
+@pytest.mark.parametrize("n,density,dense", [(58, 1.0, False), (114, 1.0, False), (300, 0.2, False), (700, 0.95, True), (1500, 0.5, True)])
 def test_gat_forward_backward(n, density, dense):
     from hic_gnn_b200 import layers as glayers
-    from oracle import conv as oconv
 
-    _, x, odata, gdata = _setup(n, density, seed=2)
-    torch.manual_seed(1)
-    oc = oconv.GATConv(512, 256, heads=2)
-    with torch.no_grad():
-        oc.bias.uniform_(-0.1, 0.1)
-        oc.att_l.mul_(3.0)  # sharper attention so the softmax is far from uniform
-        oc.att_r.mul_(3.0)
+    x, odata, gdata, oc = _gat_case(n, density)
     gc = glayers.GATConv(512, 256, heads=2).cuda()
     gc.load_state_dict(oc.state_dict())
     assert list(gc.state_dict().keys()) == ["att_l", "att_r", "bias", "lin_l.weight", "lin_r.weight"]
