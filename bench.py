@@ -246,6 +246,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def profile_region(name: str, on: bool) -> None:
+    """cudaProfilerStart/Stop around one timed region when HICGAT_PROFILE_REGION names it, so that
+    `ncu --profile-from-start off` lists exactly the launches of that region (every thread:
+    autograd's backward kernels are launched from its own thread, outside any NVTX range)."""
+    if os.environ.get("HICGAT_PROFILE_REGION") == name:
+        import torch
+
+        torch.cuda.synchronize()
+        (torch.cuda.profiler.start if on else torch.cuda.profiler.stop)()
+
+
 # ------------------------------------------------------------------------------ native arm
 def run_native(args):
     import torch
@@ -333,6 +344,7 @@ def run_native(args):
     barrier()
     launches0 = N.launch_count()
     w0 = time.time()
+    profile_region("loss", True)
     torch.cuda.nvtx.range_push("hicgat_loss")
     start.record()
     for k in range(K):
@@ -340,6 +352,7 @@ def run_native(args):
     stop.record()
     barrier()
     torch.cuda.nvtx.range_pop()
+    profile_region("loss", False)
     w1 = time.time()
     launches = N.launch_count() - launches0
     elapsed_ms = max_over_ranks(start.elapsed_time(stop))
@@ -392,6 +405,7 @@ def run_native(args):
         barrier()
         l0 = N.launch_count()
         w0 = time.time()
+        profile_region("train", True)
         torch.cuda.nvtx.range_push("hicgat_train")
         start.record()
         for _ in range(Kt):
@@ -399,6 +413,7 @@ def run_native(args):
         stop.record()
         barrier()
         torch.cuda.nvtx.range_pop()
+        profile_region("train", False)
         windows["train"] = (w0, time.time())
         t_ms = max_over_ranks(start.elapsed_time(stop))
         train_out = {"steps_per_s": Kt / (t_ms * 1e-3), "ms_per_step": t_ms / Kt, "steps": Kt, "model": "GATNetSelectiveResidualsUpdated",

@@ -431,10 +431,11 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
                          double* moments, float* grad, double* grad64, void* workspace, size_t workspace_bytes,
                          hicgat_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    HICGAT_REQUIRE(coords && target && moments && workspace, "hicgat_pairloss_fwd_bwd: null pointer");
     HICGAT_REQUIRE(n > 0 && n < (1ll << 30) && r0 >= 0 && r1 >= r0 && r1 <= n, "hicgat_pairloss_fwd_bwd: bad n/r0/r1 (%lld,%lld,%lld)", (long long)n, (long long)r0, (long long)r1);
+    // an empty row block (r0 == r1, a trailing rank of a sharded run) has no target rows to point at
+    HICGAT_REQUIRE(coords && (target || r0 == r1) && moments && workspace, "hicgat_pairloss_fwd_bwd: null pointer");
     HICGAT_REQUIRE(pitch >= n && (pitch % 4) == 0, "hicgat_pairloss_fwd_bwd: pitch %lld must be >= n and a multiple of 4", (long long)pitch);
-    HICGAT_REQUIRE(aligned16(target), "hicgat_pairloss_fwd_bwd: target must be 16-byte aligned");
+    HICGAT_REQUIRE(aligned16(target), "hicgat_pairloss_fwd_bwd: target must be 16-byte aligned");  // NULL passes
     HICGAT_REQUIRE((mode & ~7u) == 0, "hicgat_pairloss_fwd_bwd: unknown mode bits 0x%x", mode);
     HICGAT_REQUIRE(!(mode & 3u) || grad || grad64, "hicgat_pairloss_fwd_bwd: grad is NULL but a gradient mode is set");
     const Layout L = make_layout(n, r0, r1);

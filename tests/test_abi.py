@@ -28,7 +28,7 @@ def test_version_and_error_text(built):
     lib = N.lib()
     assert lib.hicgat_version() >= 100
     # argument validation happens before any CUDA call, so this is safe without a GPU
-    rc = lib.hicgat_pairloss_fwd_bwd(None, None, 0, 0, 0, 0, 0, 0.0, 0.0, None, None, None, 0, None)
+    rc = lib.hicgat_pairloss_fwd_bwd(None, None, 8, 8, 0, 8, 0, 0.0, 0.0, None, None, None, 0, None)
     assert rc == -1
     assert b"null pointer" in lib.hicgat_last_error()
     with pytest.raises(RuntimeError, match="null pointer"):
