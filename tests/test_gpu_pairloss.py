@@ -111,7 +111,7 @@ def test_row_sharded_blocks_sum_to_full_and_are_deterministic():
         m, g = ops.pairloss_raw(coords, blk, mode, 4.0 / n**2, 0.0)
         m_sum += m
         g_sum += g
-    assert rel_err(m_sum, m_full) < 1e-12
+    assert rel_err(m_sum, m_full) < 1e-8  # f32 per-thread partials are grouped differently per block
     assert rel_err(g_sum, g_full) < 1e-6
 
 
