@@ -169,6 +169,52 @@ def _loss_f64(coords, truth, mode):
     return ((d - truth.float().double()) ** 2).mean()
 
 
+_KINK_FEEDERS = {  # modules whose output goes straight into relu / leaky_relu
+    "Net": ["conv", "densea", "dense1", "dense2"],
+    "GATNetSelectiveResidualsUpdated": ["conv", "norm_a", "norm1", "norm2"],
+    "GATNetHeadsChanged3LayersLeakyReLUv2": ["conv", "densea", "dense1"],
+}
+
+
+class _KinkWatch:
+    """Smallest relative distance of any (Leaky)ReLU pre-activation of the oracle forward to its
+    kink at 0 (network activations and the GAT edge logits).  A unit closer to 0 than f32
+    rounding takes slope 1 on one side and 0 / 0.2 / 0.01 on the other purely by summation
+    order -- on the reference's side as much as on ours -- which moves the gradient of its
+    parameters by a whole term."""
+
+    def __init__(self, model, cls):
+        from oracle import conv as oconv
+        from oracle.graph import set_diag
+
+        self.gap = float("inf")
+        self.handles = []
+
+        def act_hook(mod, inp, out):
+            o = out.detach()
+            self.gap = min(self.gap, float(o.abs().min() / o.abs().max()))
+
+        def gat_hook(mod, inp, out):
+            with torch.no_grad():
+                _, al, ar = mod._project(inp[0])
+                g = set_diag(inp[1])
+                z = al[g.col] + ar[g.row]
+                self.gap = min(self.gap, float(z.abs().min() / z.abs().max()))
+
+        for name in _KINK_FEEDERS[cls]:
+            m = getattr(model, name)
+            self.handles.append(m.register_forward_hook(act_hook))
+            if isinstance(m, oconv.GATConv):
+                self.handles.append(m.register_forward_hook(gat_hook))
+
+    def reset(self):
+        self.gap = float("inf")
+
+    def close(self):
+        for h in self.handles:
+            h.remove()
+
+
 def _param_grads(model):
     return {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in model.named_parameters()}
 
@@ -203,11 +249,18 @@ def test_per_step_loss_and_gradients_along_oracle_trajectory(cls, mode, n, densi
     truth = owish.cont2dist(odata.y.clone(), 1.0)
     target = gutils.wish_target(gdata.y, 1.0)
     opt = torch.optim.Adam(om.parameters(), lr=1e-3)
+    watch = _KinkWatch(om, cls)
+    strict_steps = 0
     for s in range(steps):
         gm.load_state_dict(om.state_dict())
         # reference gradients of the f64-evaluated formula
         opt.zero_grad()
+        watch.reset()
         coords_o = om.get_model(odata.x.float(), odata.edge_index)
+        # a unit within ~10 ulp of its activation kink: its slope is decided by rounding on both
+        # sides, so that step's gradients are only checked loosely
+        tol_g = 2e-5 if watch.gap > 1e-6 else 2e-3
+        strict_steps += tol_g == 2e-5
         _loss_f64(coords_o, truth, mode).backward()
         g64 = _param_grads(om)
         # the reference's own f32 evaluation (this is what drives the oracle trajectory)
@@ -235,8 +288,10 @@ def test_per_step_loss_and_gradients_along_oracle_trajectory(cls, mode, n, densi
                 continue
             e_gpu = rel_err(p.grad, want)
             e_ref = rel_err(g32[name], want)
-            assert e_gpu < max(2e-5, e_ref), (s, name, e_gpu, e_ref)
+            assert e_gpu < max(tol_g, e_ref), (s, name, e_gpu, e_ref, watch.gap)
         opt.step()
+    watch.close()
+    assert strict_steps >= steps // 2, strict_steps
 
 
 @pytest.mark.parametrize("cls,mode,n,density", _TRAJ_CASES)
