@@ -42,7 +42,7 @@ SIGNATURES = {
     "hicgat_gat_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
-PAIR_GRAD_MSE, PAIR_GRAD_L1, PAIR_MOMENTS, PAIR_NMOM = 1, 2, 4, 8
+PAIR_GRAD_MSE, PAIR_GRAD_L1, PAIR_MOMENTS, PAIR_MOMENTS_D, PAIR_NMOM = 1, 2, 4, 8, 8
 
 _lib = None
 

@@ -5,33 +5,57 @@
 // train_and_test_same_res_GAT_node2vec.py:131-134) without materialising the N x N
 // prediction.  HBM-bound: 4 B per ordered pair (one f32 target element), d = 3.
 //
-// Work decomposition
-//   CTA  = 8 warps x (128 columns) x (RB rows); grid = (column strips, row chunks).
-//   lane = 4 consecutive columns j (one 128-bit streaming load per row), kept as two packed
-//          f32x2 pairs so the arithmetic runs on FADD2/FMUL2/FFMA2;
-//   warp = row groups of U=8 rows, interleaved over the CTA's 8 warps (8 loads in flight/lane);
-//   x_j and the column-side gradient accumulators live in registers for the whole CTA
-//   lifetime, x_i (warp-uniform) is broadcast from shared memory.
-// Because the target is symmetric the column-side sum  g_j = sum_i w_ij (x_j - x_i)  is the
-// complete gradient: no row-side reduction, no atomics.  Row chunks are combined by the last
-// CTA to finish each column strip (fixed summation order => bit-reproducible).
+// Work decomposition (both kernel variants)
+//   CTA  = 8 consumer warps x 128 columns x rb rows; grid = (column strips, row chunks).
+//   lane = 4 consecutive columns j, kept as two packed f32x2 pairs so the arithmetic runs on
+//          FADD2/FMUL2/FFMA2; x_j and the column-side gradient accumulators live in registers
+//          for the whole CTA lifetime, x_i (warp-uniform) is broadcast from shared memory.
+//   Because the target is symmetric the column-side sum  g_j = sum_i w_ij (x_j - x_i)  is the
+//   complete gradient: no row-side reduction, no atomics.  Row chunks are combined by the last
+//   CTA to finish each column strip (fixed summation order => bit-reproducible).
+//
+// Variant 0 (default, "tma"): every warp keeps a private 3-slot shared-memory ring; lane 0 issues
+//   cp.async.bulk.tensor.2d (TMA) boxes of 8 rows x 128 columns (4 KB) that complete on the
+//   warp's mbarriers and refills a slot as soon as the warp has consumed it, so no warp ever
+//   waits on a global load it issued itself and 2 CTAs x 8 warps x 3 x 4 KB = 192 KB of target
+//   are in flight per SM.  TMA zero-fills columns >= n and rows >= r1-r0 (no edge address logic).
+// Variant 1 ("ldg"): each lane issues 8 streaming 128-bit ld.global.nc per row group; kept for
+//   A/B measurements and as the path used when a tensor map cannot be encoded.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is resolved through cudart at run time)
+
 #include "common.cuh"
 
 namespace hicgat {
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
-constexpr int kCols = 128;  // columns per CTA strip (32 lanes x 4)
-constexpr int kU = 8;       // rows per group (loads in flight per lane)
+constexpr int kWarps = 8;                 // consumer warps
+constexpr int kThreads = kWarps * 32;     // variant 1 block size
+constexpr int kCols = 128;                // columns per CTA strip (32 lanes x 4)
+constexpr int kU = 8;                     // rows per warp per group / tile
 constexpr int kNM = HICGAT_PAIR_NMOM;
+constexpr int kTileRows = kWarps * kU;    // 64 rows per CTA tile step (8 per warp)
+constexpr int kStages = 3;                // TMA slots per warp
+constexpr int kSubTileBytes = kU * kCols * 4;               // 4096: one warp's 8 rows x 128 columns
+constexpr int kSlotBytes = kSubTileBytes + 256;             // + (x,x,y,y) x8 + (z,z) x8, padded to 128 B
+constexpr int kTmaSmem = kWarps * kStages * kSlotBytes + 128;  // 104576 B: two CTAs per SM
+
+// which upper-triangle statistics are accumulated
+constexpr uint32_t kMomFull = HICGAT_PAIR_MOMENTS;          // everything (sum t, sum t^2, sum |d-t| too)
+constexpr uint32_t kMomLight = HICGAT_PAIR_MOMENTS_D;       // sum d, sum d^2, sum d t, sum (d-t)^2 only
 
 struct Acc {
     f2 gx[2], gy[2], gz[2];          // column-side gradient, 2 column pairs
-    f2 see;                          // sum (d-t)^2, all pairs
+    f2 see;                          // sum (d-t)^2 over pairs NOT counted in seu
     f2 sd, sdd, st, stt, sdt, seu;   // upper-triangle moments
     float sabs0, sabs1;              // upper-triangle sum |d-t|
 };
+
+__device__ __forceinline__ void acc_zero(Acc& a) {
+#pragma unroll
+    for (int p = 0; p < 2; ++p) a.gx[p] = a.gy[p] = a.gz[p] = 0ull;
+    a.see = a.sd = a.sdd = a.st = a.stt = a.sdt = a.seu = 0ull;
+    a.sabs0 = a.sabs1 = 0.f;
+}
 
 template <uint32_t MODE>
 __device__ __forceinline__ f2 grad_weight(f2 e, f2 rs, float c_mse, float c_l1) {
@@ -52,69 +76,82 @@ __device__ __forceinline__ f2 grad_weight(f2 e, f2 rs, float c_mse, float c_l1) 
     }
 }
 
+// d^2 + 1e-30: keeps rsqrt finite on the diagonal / for coincident loci (d = 1e-15, weight * 0 = 0,
+// matching ATen's "ratio = 0 where dist == 0") at the cost of nothing: it rides in the first FMA.
+#define HICGAT_TINY2 0x0DA242600DA24260ull /* (1e-30f, 1e-30f) */
+
 // One row x one column pair, no masks.  UPPER: this (row, pair) lies strictly above the diagonal.
 template <uint32_t MODE, bool UPPER>
 __device__ __forceinline__ void pair_fast(Acc& a, int p, f2 xjx, f2 xjy, f2 xjz, f2 xix, f2 xiy,
                                           f2 xiz, f2 t, float c_mse, float c_l1) {
     f2 dx = f2_sub(xjx, xix), dy = f2_sub(xjy, xiy), dz = f2_sub(xjz, xiz);
-    f2 d2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+    f2 d2 = f2_fma(dx, dx, f2_fma(dy, dy, f2_fma(dz, dz, HICGAT_TINY2)));
     float d2a, d2b;
     f2_unpack(d2, d2a, d2b);
-    f2 rs = f2_pack(rsqrt_approx(fmaxf(d2a, 1e-30f)), rsqrt_approx(fmaxf(d2b, 1e-30f)));
+    f2 rs = f2_pack(rsqrt_approx(d2a), rsqrt_approx(d2b));
     f2 d = f2_mul(d2, rs);
     f2 e = f2_sub(d, t);
-    a.see = f2_fma(e, e, a.see);
+    constexpr bool kMom = UPPER && (MODE & (kMomFull | kMomLight));
+    if constexpr (kMom) a.seu = f2_fma(e, e, a.seu);
+    else a.see = f2_fma(e, e, a.see);
     if constexpr ((MODE & 3u) != 0) {
         f2 w = grad_weight<MODE>(e, rs, c_mse, c_l1);
         a.gx[p] = f2_fma(w, dx, a.gx[p]);
         a.gy[p] = f2_fma(w, dy, a.gy[p]);
         a.gz[p] = f2_fma(w, dz, a.gz[p]);
     }
-    if constexpr (UPPER && (MODE & HICGAT_PAIR_MOMENTS)) {
-        float ea, eb;
-        f2_unpack(e, ea, eb);
-        a.sabs0 += fabsf(ea);
-        a.sabs1 += fabsf(eb);
+    if constexpr (kMom) {
         a.sd = f2_add(a.sd, d);
         a.sdd = f2_add(a.sdd, d2);
-        a.st = f2_add(a.st, t);
-        a.stt = f2_fma(t, t, a.stt);
         a.sdt = f2_fma(d, t, a.sdt);
-        a.seu = f2_fma(e, e, a.seu);
+        if constexpr ((MODE & kMomFull) != 0) {
+            float ea, eb;
+            f2_unpack(e, ea, eb);
+            a.sabs0 += fabsf(ea);
+            a.sabs1 += fabsf(eb);
+            a.st = f2_add(a.st, t);
+            a.stt = f2_fma(t, t, a.stt);
+        }
     }
 }
 
-// Masked variant for edge strips (columns >= n) and diagonal-crossing groups.
-// mv: 1 for valid columns; mu: 1 where additionally row < col.
+// Masked variant for edge strips (columns >= n), partial tiles and diagonal-crossing groups.
+// mv: 1 for valid (row, column); mu: 1 where additionally row < col.
 template <uint32_t MODE>
 __device__ __forceinline__ void pair_masked(Acc& a, int p, f2 xjx, f2 xjy, f2 xjz, f2 xix, f2 xiy,
                                             f2 xiz, f2 t, f2 mv, f2 mu, float c_mse, float c_l1) {
     f2 dx = f2_sub(xjx, xix), dy = f2_sub(xjy, xiy), dz = f2_sub(xjz, xiz);
-    f2 d2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+    f2 d2 = f2_fma(dx, dx, f2_fma(dy, dy, f2_fma(dz, dz, HICGAT_TINY2)));
     float d2a, d2b;
     f2_unpack(d2, d2a, d2b);
-    f2 rs = f2_pack(rsqrt_approx(fmaxf(d2a, 1e-30f)), rsqrt_approx(fmaxf(d2b, 1e-30f)));
+    f2 rs = f2_pack(rsqrt_approx(d2a), rsqrt_approx(d2b));
     f2 d = f2_mul(d2, rs);
     f2 e = f2_mul(f2_sub(d, t), mv);
-    a.see = f2_fma(e, e, a.see);
+    constexpr bool kMom = (MODE & (kMomFull | kMomLight)) != 0;
     if constexpr ((MODE & 3u) != 0) {
         f2 w = f2_mul(grad_weight<MODE>(e, rs, c_mse, c_l1), mv);
         a.gx[p] = f2_fma(w, dx, a.gx[p]);
         a.gy[p] = f2_fma(w, dy, a.gy[p]);
         a.gz[p] = f2_fma(w, dz, a.gz[p]);
     }
-    if constexpr ((MODE & HICGAT_PAIR_MOMENTS) != 0) {
+    if constexpr (kMom) {
         f2 eu = f2_mul(e, mu), du = f2_mul(d, mu), tu = f2_mul(t, mu);
-        float ea, eb;
-        f2_unpack(eu, ea, eb);
-        a.sabs0 += fabsf(ea);
-        a.sabs1 += fabsf(eb);
+        f2 el = f2_sub(e, eu);  // the part of e not under the upper mask
+        a.see = f2_fma(el, el, a.see);
+        a.seu = f2_fma(eu, eu, a.seu);
         a.sd = f2_add(a.sd, du);
         a.sdd = f2_fma(du, du, a.sdd);
-        a.st = f2_add(a.st, tu);
-        a.stt = f2_fma(tu, tu, a.stt);
         a.sdt = f2_fma(du, tu, a.sdt);
-        a.seu = f2_fma(eu, eu, a.seu);
+        if constexpr ((MODE & kMomFull) != 0) {
+            float ea, eb;
+            f2_unpack(eu, ea, eb);
+            a.sabs0 += fabsf(ea);
+            a.sabs1 += fabsf(eb);
+            a.st = f2_add(a.st, tu);
+            a.stt = f2_fma(tu, tu, a.stt);
+        }
+    } else {
+        a.see = f2_fma(e, e, a.see);
     }
 }
 
@@ -133,110 +170,77 @@ struct Params {
     unsigned* done_count;  // [1]
 };
 
-template <uint32_t MODE>
-__global__ void __launch_bounds__(kThreads, 2) pairloss_kernel(const Params P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* s_xy = reinterpret_cast<float4*>(smem_raw);                  // [rb] (x,x,y,y)
-    float2* s_z = reinterpret_cast<float2*>(smem_raw + sizeof(float4) * P.rb);  // [rb] (z,z)
-    __shared__ float s_g[kWarps][kCols * 3 + 4];
-    __shared__ double s_m[kWarps][kNM];
-    __shared__ unsigned s_ticket[2];
+struct ColumnRegs {
+    f2 xjx[2], xjy[2], xjz[2], mv[2];
+};
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int strip = blockIdx.x, chunk = blockIdx.y;
-    const int n = P.n;
-    const int col0 = strip * kCols + lane * 4;
-    const int row_begin = P.r0 + chunk * P.rb;
-    const int row_end = min(row_begin + P.rb, P.r1);
-    const int nrows = row_end - row_begin;
-    const bool edge = (strip + 1) * kCols > n;
-
-    // stage this chunk's row coordinates, duplicated for packed broadcast
-    for (int r = threadIdx.x; r < nrows; r += kThreads) {
-        const float* c = P.coords + (size_t)(row_begin + r) * 3;
-        float x = c[0], y = c[1], z = c[2];
-        s_xy[r] = make_float4(x, x, y, y);
-        s_z[r] = make_float2(z, z);
-    }
-    // this lane's 4 columns
+__device__ __forceinline__ void load_columns(ColumnRegs& c, const float* __restrict__ coords, int col0, int n) {
     float cj[4][3];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        int c = min(col0 + k, n - 1);
+        int cc = min(col0 + k, n - 1);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) cj[k][q] = P.coords[(size_t)c * 3 + q];
+        for (int q = 0; q < 3; ++q) cj[k][q] = coords[(size_t)cc * 3 + q];
     }
-    f2 xjx[2], xjy[2], xjz[2], mv[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        xjx[p] = f2_pack(cj[2 * p][0], cj[2 * p + 1][0]);
-        xjy[p] = f2_pack(cj[2 * p][1], cj[2 * p + 1][1]);
-        xjz[p] = f2_pack(cj[2 * p][2], cj[2 * p + 1][2]);
-        mv[p] = f2_pack(col0 + 2 * p < n ? 1.f : 0.f, col0 + 2 * p + 1 < n ? 1.f : 0.f);
+        c.xjx[p] = f2_pack(cj[2 * p][0], cj[2 * p + 1][0]);
+        c.xjy[p] = f2_pack(cj[2 * p][1], cj[2 * p + 1][1]);
+        c.xjz[p] = f2_pack(cj[2 * p][2], cj[2 * p + 1][2]);
+        c.mv[p] = f2_pack(col0 + 2 * p < n ? 1.f : 0.f, col0 + 2 * p + 1 < n ? 1.f : 0.f);
     }
-    Acc a;
-#pragma unroll
-    for (int p = 0; p < 2; ++p) a.gx[p] = a.gy[p] = a.gz[p] = 0ull;
-    a.see = a.sd = a.sdd = a.st = a.stt = a.sdt = a.seu = 0ull;
-    a.sabs0 = a.sabs1 = 0.f;
-    __syncthreads();
+}
 
-    const bool can_load = col0 + 3 < P.pitch;  // pitch is a multiple of 4
-    const float* tbase = P.target + (size_t)(row_begin - P.r0) * P.pitch + col0;
-    const int strip_lo = strip * kCols, strip_hi = strip_lo + kCols - 1;
-    const int ngroups = (nrows + kU - 1) / kU;
-
-    for (int g = warp; g < ngroups; g += kWarps) {
-        const int rl = g * kU;                      // local row of the group
-        const int rows_here = min(kU, nrows - rl);
-        const int rg = row_begin + rl;              // global row
-        float4 t[kU];
-        if (rows_here == kU && can_load) {
+// kU rows of one warp: t[u] = the lane's 4 target values of row (rg + u); xi from shared memory.
+template <uint32_t MODE>
+__device__ __forceinline__ void process_group(Acc& a, const ColumnRegs& c, const float4 (&t)[kU], const float4* __restrict__ s_xy,
+                                              const float2* __restrict__ s_z, int rows_here, int rg, int col0, int n, bool edge,
+                                              int strip_lo, int strip_hi, float c_mse, float c_l1) {
+    const bool fast = !edge && rows_here == kU;
+    if (fast && rg + kU - 1 < strip_lo) {  // strictly above the diagonal
 #pragma unroll
-            for (int u = 0; u < kU; ++u) t[u] = ldg_stream_f4(tbase + (size_t)(rl + u) * P.pitch);
-        } else {
-#pragma unroll
-            for (int u = 0; u < kU; ++u)
-                t[u] = (u < rows_here && can_load) ? ldg_stream_f4(tbase + (size_t)(rl + u) * P.pitch)
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < kU; ++u) {
+            float4 xy = s_xy[u];
+            float2 zz = s_z[u];
+            f2 xix = f2_pack(xy.x, xy.y), xiy = f2_pack(xy.z, xy.w), xiz = f2_pack(zz.x, zz.y);
+            pair_fast<MODE, true>(a, 0, c.xjx[0], c.xjy[0], c.xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), c_mse, c_l1);
+            pair_fast<MODE, true>(a, 1, c.xjx[1], c.xjy[1], c.xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), c_mse, c_l1);
         }
-        const bool fast = !edge && rows_here == kU;
-        if (fast && rg + kU - 1 < strip_lo) {  // strictly above the diagonal
+    } else if (fast && rg > strip_hi) {    // strictly below
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                float4 xy = s_xy[rl + u];
-                float2 zz = s_z[rl + u];
+        for (int u = 0; u < kU; ++u) {
+            float4 xy = s_xy[u];
+            float2 zz = s_z[u];
+            f2 xix = f2_pack(xy.x, xy.y), xiy = f2_pack(xy.z, xy.w), xiz = f2_pack(zz.x, zz.y);
+            pair_fast<MODE, false>(a, 0, c.xjx[0], c.xjy[0], c.xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), c_mse, c_l1);
+            pair_fast<MODE, false>(a, 1, c.xjx[1], c.xjy[1], c.xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), c_mse, c_l1);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (u < rows_here) {
+                const int r = rg + u;
+                float4 xy = s_xy[u];
+                float2 zz = s_z[u];
                 f2 xix = f2_pack(xy.x, xy.y), xiy = f2_pack(xy.z, xy.w), xiz = f2_pack(zz.x, zz.y);
-                pair_fast<MODE, true>(a, 0, xjx[0], xjy[0], xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), P.c_mse, P.c_l1);
-                pair_fast<MODE, true>(a, 1, xjx[1], xjy[1], xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), P.c_mse, P.c_l1);
-            }
-        } else if (fast && rg > strip_hi) {    // strictly below
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                float4 xy = s_xy[rl + u];
-                float2 zz = s_z[rl + u];
-                f2 xix = f2_pack(xy.x, xy.y), xiy = f2_pack(xy.z, xy.w), xiz = f2_pack(zz.x, zz.y);
-                pair_fast<MODE, false>(a, 0, xjx[0], xjy[0], xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), P.c_mse, P.c_l1);
-                pair_fast<MODE, false>(a, 1, xjx[1], xjy[1], xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), P.c_mse, P.c_l1);
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                if (u < rows_here) {
-                    const int r = rg + u;
-                    float4 xy = s_xy[rl + u];
-                    float2 zz = s_z[rl + u];
-                    f2 xix = f2_pack(xy.x, xy.y), xiy = f2_pack(xy.z, xy.w), xiz = f2_pack(zz.x, zz.y);
-                    f2 mu0 = f2_pack((col0 + 0 < n && r < col0 + 0) ? 1.f : 0.f, (col0 + 1 < n && r < col0 + 1) ? 1.f : 0.f);
-                    f2 mu1 = f2_pack((col0 + 2 < n && r < col0 + 2) ? 1.f : 0.f, (col0 + 3 < n && r < col0 + 3) ? 1.f : 0.f);
-                    pair_masked<MODE>(a, 0, xjx[0], xjy[0], xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), mv[0], mu0, P.c_mse, P.c_l1);
-                    pair_masked<MODE>(a, 1, xjx[1], xjy[1], xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), mv[1], mu1, P.c_mse, P.c_l1);
-                }
+                f2 mu0 = f2_pack((col0 + 0 < n && r < col0 + 0) ? 1.f : 0.f, (col0 + 1 < n && r < col0 + 1) ? 1.f : 0.f);
+                f2 mu1 = f2_pack((col0 + 2 < n && r < col0 + 2) ? 1.f : 0.f, (col0 + 3 < n && r < col0 + 3) ? 1.f : 0.f);
+                pair_masked<MODE>(a, 0, c.xjx[0], c.xjy[0], c.xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), c.mv[0], mu0, c_mse, c_l1);
+                pair_masked<MODE>(a, 1, c.xjx[1], c.xjy[1], c.xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), c.mv[1], mu1, c_mse, c_l1);
             }
         }
     }
+}
 
-    // ---- CTA combine: gradients (fixed warp order) and moments (f64) ----
+struct CombineSmem {
+    float g[kWarps][kCols * 3 + 4];
+    double m[kWarps][kNM];
+    unsigned ticket[2];
+};
+
+// warp-level part of the CTA combine: park this warp's gradients / moments in shared memory
+template <uint32_t MODE>
+__device__ __forceinline__ void park_warp(const Acc& a, CombineSmem& S, int warp, int lane) {
     if constexpr ((MODE & 3u) != 0) {
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
@@ -244,68 +248,75 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_kernel(const Params P) {
             f2_unpack(a.gx[p], x0, x1);
             f2_unpack(a.gy[p], y0, y1);
             f2_unpack(a.gz[p], z0, z1);
-            float* dst = &s_g[warp][(lane * 4 + 2 * p) * 3];
+            float* dst = &S.g[warp][(lane * 4 + 2 * p) * 3];
             dst[0] = x0; dst[1] = y0; dst[2] = z0;
             dst[3] = x1; dst[4] = y1; dst[5] = z1;
         }
     }
-    {
-        double m[kNM];
-        m[0] = (double)f2_hsum(a.see);
-        if constexpr ((MODE & HICGAT_PAIR_MOMENTS) != 0) {
+    constexpr bool kMom = (MODE & (kMomFull | kMomLight)) != 0;
+    double m[kNM];
+#pragma unroll
+    for (int k = 0; k < kNM; ++k) m[k] = 0.0;
+    const double seu = (double)f2_hsum(a.seu);
+    m[0] = (double)f2_hsum(a.see) + seu;
+    if constexpr (kMom) {
+        m[2] = (double)f2_hsum(a.sd);
+        m[3] = (double)f2_hsum(a.sdd);
+        m[6] = (double)f2_hsum(a.sdt);
+        m[7] = seu;
+        if constexpr ((MODE & kMomFull) != 0) {
             m[1] = (double)a.sabs0 + (double)a.sabs1;
-            m[2] = (double)f2_hsum(a.sd);
-            m[3] = (double)f2_hsum(a.sdd);
             m[4] = (double)f2_hsum(a.st);
             m[5] = (double)f2_hsum(a.stt);
-            m[6] = (double)f2_hsum(a.sdt);
-            m[7] = (double)f2_hsum(a.seu);
-        } else {
-#pragma unroll
-            for (int k = 1; k < kNM; ++k) m[k] = 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < kNM; ++k) {
-            if (k == 0 || (MODE & HICGAT_PAIR_MOMENTS)) m[k] = warp_sum(m[k]);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < kNM; ++k) s_m[warp][k] = m[k];
         }
     }
-    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kNM; ++k) {
+        if (k == 0 || kMom) m[k] = warp_sum(m[k]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kNM; ++k) S.m[warp][k] = m[k];
+    }
+}
+
+// CTA-level combine + cross-CTA fixed-order reduction.  Called by ALL threads of the block after
+// a __syncthreads() that follows park_warp(); nthreads = blockDim.x.
+template <uint32_t MODE>
+__device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int strip, int chunk, int tid, int nthreads) {
+    const int n = P.n;
     const int cta = chunk * P.nstrips + strip;
     if constexpr ((MODE & 3u) != 0) {
         float* gp = P.gpart + (size_t)cta * (kCols * 3);
-        for (int i = threadIdx.x; i < kCols * 3; i += kThreads) {
+        for (int i = tid; i < kCols * 3; i += nthreads) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) s += s_g[w][i];
+            for (int w = 0; w < kWarps; ++w) s += S.g[w][i];
             __stcg(gp + i, s);
         }
     }
-    if (threadIdx.x < kNM) {
+    if (tid < kNM) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += s_m[w][threadIdx.x];
-        __stcg(P.mpart + (size_t)cta * kNM + threadIdx.x, s);
+        for (int w = 0; w < kWarps; ++w) s += S.m[w][tid];
+        __stcg(P.mpart + (size_t)cta * kNM + tid, s);
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        s_ticket[0] = atomicAdd(P.strip_count + strip, 1u);
-        s_ticket[1] = atomicAdd(P.done_count, 1u);
+    if (tid == 0) {
+        S.ticket[0] = atomicAdd(P.strip_count + strip, 1u);
+        S.ticket[1] = atomicAdd(P.done_count, 1u);
     }
     __syncthreads();
-    const bool last_in_strip = s_ticket[0] == (unsigned)(P.nchunks - 1);
-    const bool last_overall = s_ticket[1] == (unsigned)(P.nchunks * P.nstrips - 1);
+    const bool last_in_strip = S.ticket[0] == (unsigned)(P.nchunks - 1);
+    const bool last_overall = S.ticket[1] == (unsigned)(P.nchunks * P.nstrips - 1);
     if (!last_in_strip && !last_overall) return;
     __threadfence();
     if constexpr ((MODE & 3u) != 0) {
         if (last_in_strip) {
             const float scale = ((MODE & 3u) == HICGAT_PAIR_GRAD_MSE) ? P.c_mse
                                 : ((MODE & 3u) == HICGAT_PAIR_GRAD_L1) ? P.c_l1 : 1.f;
-            for (int i = threadIdx.x; i < kCols * 3; i += kThreads) {
+            for (int i = tid; i < kCols * 3; i += nthreads) {
                 double s = 0.0;
                 for (int c = 0; c < P.nchunks; ++c)
                     s += (double)__ldcg(P.gpart + ((size_t)c * P.nstrips + strip) * (kCols * 3) + i);
@@ -319,30 +330,202 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_kernel(const Params P) {
         }
     }
     if (last_overall) {
-        // fixed-order f64 reduction of all CTA moment partials
-        __shared__ double s_red[kThreads / 32][kNM];
+        // fixed-order f64 reduction of all CTA moment partials (S.m is free again: every thread
+        // passed the barrier above after reading it)
         double m[kNM];
 #pragma unroll
         for (int k = 0; k < kNM; ++k) m[k] = 0.0;
         const int total = P.nchunks * P.nstrips;
-        for (int c = threadIdx.x; c < total; c += kThreads) {
+        if (tid < kThreads) {
+            for (int c = tid; c < total; c += kThreads) {
 #pragma unroll
-            for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.mpart + (size_t)c * kNM + k);
-        }
+                for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.mpart + (size_t)c * kNM + k);
+            }
 #pragma unroll
-        for (int k = 0; k < kNM; ++k) m[k] = warp_sum(m[k]);
-        if (lane == 0) {
+            for (int k = 0; k < kNM; ++k) m[k] = warp_sum(m[k]);
+            if ((tid & 31) == 0) {
 #pragma unroll
-            for (int k = 0; k < kNM; ++k) s_red[warp][k] = m[k];
+                for (int k = 0; k < kNM; ++k) S.m[tid >> 5][k] = m[k];
+            }
         }
         __syncthreads();
-        if (threadIdx.x < kNM) {
+        if (tid < kNM) {
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) s += s_red[w][threadIdx.x];
-            P.moments[threadIdx.x] = s;
+            for (int w = 0; w < kWarps; ++w) s += S.m[w][tid];
+            P.moments[tid] = s;
         }
     }
+}
+
+// ------------------------------------------------------------------ variant 1: per-lane streaming loads
+template <uint32_t MODE>
+__global__ void __launch_bounds__(kThreads, 2) pairloss_ldg_kernel(const Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_xy = reinterpret_cast<float4*>(smem_raw);                          // [rb] (x,x,y,y)
+    float2* s_z = reinterpret_cast<float2*>(smem_raw + sizeof(float4) * P.rb);   // [rb] (z,z)
+    __shared__ CombineSmem S;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x, chunk = blockIdx.y;
+    const int n = P.n;
+    const int col0 = strip * kCols + lane * 4;
+    const int row_begin = P.r0 + chunk * P.rb;
+    const int row_end = min(row_begin + P.rb, P.r1);
+    const int nrows = row_end - row_begin;
+    const bool edge = (strip + 1) * kCols > n;
+
+    for (int r = threadIdx.x; r < nrows; r += kThreads) {
+        const float* c = P.coords + (size_t)(row_begin + r) * 3;
+        float x = c[0], y = c[1], z = c[2];
+        s_xy[r] = make_float4(x, x, y, y);
+        s_z[r] = make_float2(z, z);
+    }
+    ColumnRegs c;
+    load_columns(c, P.coords, col0, n);
+    Acc a;
+    acc_zero(a);
+    __syncthreads();
+
+    const bool can_load = col0 + 3 < P.pitch;  // pitch is a multiple of 4
+    const float* tbase = P.target + (size_t)(row_begin - P.r0) * P.pitch + col0;
+    const int strip_lo = strip * kCols, strip_hi = strip_lo + kCols - 1;
+    const int ngroups = (nrows + kU - 1) / kU;
+
+    for (int g = warp; g < ngroups; g += kWarps) {
+        const int rl = g * kU;
+        const int rows_here = min(kU, nrows - rl);
+        float4 t[kU];
+        if (rows_here == kU && can_load) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) t[u] = ldg_stream_f4(tbase + (size_t)(rl + u) * P.pitch);
+        } else {
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                t[u] = (u < rows_here && can_load) ? ldg_stream_f4(tbase + (size_t)(rl + u) * P.pitch)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        process_group<MODE>(a, c, t, s_xy + rl, s_z + rl, rows_here, row_begin + rl, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1);
+    }
+    park_warp<MODE>(a, S, warp, lane);
+    __syncthreads();
+    finish_cta<MODE>(P, S, strip, chunk, threadIdx.x, kThreads);
+}
+
+// ------------------------------------------------------------------ variant 0: TMA + mbarrier ring
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Every consumer warp runs its OWN ring: lane 0 issues a TMA box of 8 rows x 128 columns (4 KB)
+// per stage for the warp's rows of tile t and refills the slot right after the warp has consumed
+// it -- no producer warp, no empty barriers, no cross-warp synchronisation in the main loop.
+template <uint32_t MODE>
+__global__ void __launch_bounds__(kThreads, 2) pairloss_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params P) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    __shared__ __align__(8) uint64_t full_bar[kWarps][kStages];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x, chunk = blockIdx.y;
+    const int n = P.n;
+    const int row_begin = P.r0 + chunk * P.rb;
+    const int row_end = min(row_begin + P.rb, P.r1);
+    const int nrows = row_end - row_begin;
+    const int ntiles = (nrows + kTileRows - 1) / kTileRows;
+    const int col0 = strip * kCols + lane * 4;
+    const bool edge = (strip + 1) * kCols > n;
+    const int strip_lo = strip * kCols, strip_hi = strip_lo + kCols - 1;
+    unsigned char* wring = ring + (size_t)warp * (kStages * kSlotBytes);   // this warp's slots
+    const int wrow = warp * kU;                                             // this warp's rows inside a tile
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    }
+    __syncwarp();
+
+    // x_i staging: lane k < 24 owns component k%3 of row k/3 and writes it duplicated (v,v)
+    const int xi_row = lane / 3, xi_comp = lane - xi_row * 3;
+    auto xi_fetch = [&](int t) -> float {
+        const int gr = min(row_begin + t * kTileRows + wrow + xi_row, n - 1);
+        return lane < 24 ? __ldg(P.coords + (size_t)gr * 3 + xi_comp) : 0.f;
+    };
+    auto xi_store = [&](int s, float v) {
+        if (lane < 24) {
+            unsigned char* slot = wring + (size_t)s * kSlotBytes + kSubTileBytes;
+            float2* dst = xi_comp < 2 ? reinterpret_cast<float2*>(slot + xi_row * 16 + xi_comp * 8)
+                                      : reinterpret_cast<float2*>(slot + kU * 16 + xi_row * 8);
+            *dst = make_float2(v, v);
+        }
+    };
+    auto issue = [&](int t, int s) {  // lane 0 only
+        mbar_arrive_expect_tx(&full_bar[warp][s], (uint32_t)kSubTileBytes);
+        tma_load_2d(wring + (size_t)s * kSlotBytes, &tmap, strip * kCols, (row_begin - P.r0) + t * kTileRows + wrow, &full_bar[warp][s]);
+    };
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+        if (s < ntiles) {
+            if (lane == 0) issue(s, s);
+            xi_store(s, xi_fetch(s));
+        }
+    }
+    ColumnRegs c;
+    load_columns(c, P.coords, col0, n);
+    Acc a;
+    acc_zero(a);
+    __syncwarp();
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % kStages, use = t / kStages;
+        const bool refill = t + kStages < ntiles;
+        const float xi_next = refill ? xi_fetch(t + kStages) : 0.f;   // in flight during the compute below
+        mbar_wait(&full_bar[warp][s], (uint32_t)(use & 1));
+        const unsigned char* slot = wring + (size_t)s * kSlotBytes;
+        const float4* tile = reinterpret_cast<const float4*>(slot);
+        const float4* s_xy = reinterpret_cast<const float4*>(slot + kSubTileBytes);
+        const float2* s_z = reinterpret_cast<const float2*>(slot + kSubTileBytes + kU * 16);
+        const int rows_here = max(0, min(kU, nrows - (t * kTileRows + wrow)));
+        float4 tv[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) tv[u] = tile[u * (kCols / 4) + lane];
+        process_group<MODE>(a, c, tv, s_xy, s_z, rows_here, row_begin + t * kTileRows + wrow, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1);
+        __syncwarp();  // every lane is done with slot s
+        if (refill) {
+            if (lane == 0) issue(t + kStages, s);
+            xi_store(s, xi_next);
+        }
+    }
+    __syncthreads();  // all rings drained: the dynamic shared memory is reused for the combine
+    CombineSmem& S = *reinterpret_cast<CombineSmem*>(ring);
+    park_warp<MODE>(a, S, warp, lane);
+    __syncthreads();
+    finish_cta<MODE>(P, S, strip, chunk, threadIdx.x, kThreads);
 }
 
 // ------------------------------------------------------------------ materialising variant
@@ -376,10 +559,20 @@ __global__ void pairdist_bwd_kernel(const float* __restrict__ coords, int n, con
     if (lane == 0) { gc[i * 3] = gx; gc[i * 3 + 1] = gy; gc[i * 3 + 2] = gz; }
 }
 
+// ------------------------------------------------------------------ host side
 int g_rows_per_cta = 0;
+int g_variant = 0;  // 0 = TMA ring (default), 1 = per-lane streaming loads
 
-int pick_rows_per_cta(int64_t nrows, int nstrips) {
-    if (g_rows_per_cta > 0) return g_rows_per_cta;
+int pick_rows_per_cta(int64_t nrows, int nstrips, int variant) {
+    if (g_rows_per_cta > 0) return variant == 0 ? (g_rows_per_cta + kTileRows - 1) / kTileRows * kTileRows : g_rows_per_cta;
+    if (variant == 0) {
+        // long row chunks amortise the ring fill (3 tiles) and the per-CTA combine; keep >= 4 waves
+        // of 2 CTAs x 148 SMs so the tail stays short
+        const int64_t want = 148 * 2 * 4;
+        int rb = 4096;
+        while (rb > kTileRows && (int64_t)nstrips * ((nrows + rb - 1) / rb) < want) rb >>= 1;
+        return rb;
+    }
     // largest chunk that still gives >= ~6 CTAs per SM (148 SMs); bounds the partial buffers
     const int64_t want = 148 * 6;
     int rb = 1024;
@@ -392,11 +585,11 @@ struct Layout {
     size_t off_counts, off_gpart, off_mpart, total;
 };
 
-Layout make_layout(int64_t n, int64_t r0, int64_t r1) {
+Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant) {
     Layout L;
     L.nstrips = (int)((n + kCols - 1) / kCols);
     const int64_t nrows = r1 - r0;
-    L.rb = pick_rows_per_cta(nrows, L.nstrips);
+    L.rb = pick_rows_per_cta(nrows, L.nstrips, variant);
     L.nchunks = (int)((nrows + L.rb - 1) / L.rb);
     if (L.nchunks < 1) L.nchunks = 1;
     L.off_counts = 0;
@@ -406,24 +599,75 @@ Layout make_layout(int64_t n, int64_t r0, int64_t r1) {
     return L;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 2-D map over this rank's target rows: dim0 = n valid columns (pitch only enters the stride, so
+// padding columns are never read and columns >= n are zero-filled), dim1 = r1 - r0 rows.
+bool make_target_map(CUtensorMap* map, const float* target, int64_t pitch, int64_t n, int64_t nrows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)nrows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kCols, (cuuint32_t)kU};
+    const cuuint32_t estride[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(target), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <uint32_t MODE>
+cudaError_t launch_mode(int variant, const CUtensorMap& map, const Params& P, dim3 grid, cudaStream_t stream) {
+    if (variant == 0) {
+        static bool attr_set = false;  // opt in to > 48 KB dynamic shared memory once per instantiation
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(pairloss_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        pairloss_tma_kernel<MODE><<<grid, kThreads, kTmaSmem, stream>>>(map, P);
+    } else {
+        const size_t smem = (sizeof(float4) + sizeof(float2)) * (size_t)P.rb;
+        pairloss_ldg_kernel<MODE><<<grid, kThreads, smem, stream>>>(P);
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace
 }  // namespace hicgat
 
 using namespace hicgat;
 
 extern "C" int hicgat_pairloss_set_tuning(int rows_per_cta, int variant) {
-    (void)variant;
     if (rows_per_cta != 0 && (rows_per_cta < 8 || rows_per_cta > 4096 || (rows_per_cta % 8) != 0)) {
         set_error("hicgat_pairloss_set_tuning: rows_per_cta must be 0 or a multiple of 8 in [8,4096]");
         return HICGAT_ERR_INVALID;
     }
+    if (variant != 0 && variant != 1) {
+        set_error("hicgat_pairloss_set_tuning: variant must be 0 (TMA ring) or 1 (per-lane loads)");
+        return HICGAT_ERR_INVALID;
+    }
     g_rows_per_cta = rows_per_cta;
+    g_variant = variant;
     return HICGAT_OK;
 }
 
 extern "C" size_t hicgat_pairloss_workspace_bytes(int64_t n, int64_t r0, int64_t r1) {
     if (n <= 0 || r0 < 0 || r1 < r0 || r1 > n) return 0;
-    return make_layout(n, r0, r1).total;  // for the CURRENT tuning; re-query after set_tuning
+    // for the CURRENT tuning (re-query after set_tuning); covers either variant
+    const size_t a = make_layout(n, r0, r1, 0).total, b = make_layout(n, r0, r1, 1).total;
+    return a > b ? a : b;
 }
 
 static int pairloss_impl(const float* coords, const float* target, int64_t pitch, int64_t n,
@@ -436,9 +680,16 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     HICGAT_REQUIRE(coords && (target || r0 == r1) && moments && workspace, "hicgat_pairloss_fwd_bwd: null pointer");
     HICGAT_REQUIRE(pitch >= n && (pitch % 4) == 0, "hicgat_pairloss_fwd_bwd: pitch %lld must be >= n and a multiple of 4", (long long)pitch);
     HICGAT_REQUIRE(aligned16(target), "hicgat_pairloss_fwd_bwd: target must be 16-byte aligned");  // NULL passes
-    HICGAT_REQUIRE((mode & ~7u) == 0, "hicgat_pairloss_fwd_bwd: unknown mode bits 0x%x", mode);
+    HICGAT_REQUIRE((mode & ~15u) == 0, "hicgat_pairloss_fwd_bwd: unknown mode bits 0x%x", mode);
+    if (mode & HICGAT_PAIR_MOMENTS) mode &= ~HICGAT_PAIR_MOMENTS_D;          // full moments include the light set
+    if ((mode & HICGAT_PAIR_MOMENTS_D) && (mode & HICGAT_PAIR_GRAD_L1)) {     // the L1 value needs sum |d-t|: full set
+        mode = (mode & ~HICGAT_PAIR_MOMENTS_D) | HICGAT_PAIR_MOMENTS;
+    }
     HICGAT_REQUIRE(!(mode & 3u) || grad || grad64, "hicgat_pairloss_fwd_bwd: grad is NULL but a gradient mode is set");
-    const Layout L = make_layout(n, r0, r1);
+    int variant = g_variant;
+    CUtensorMap map;
+    if (variant == 0 && r1 > r0 && !make_target_map(&map, target, pitch, n, r1 - r0)) variant = 1;
+    const Layout L = make_layout(n, r0, r1, variant);
     if (workspace_bytes < L.total) {
         set_error("hicgat_pairloss_fwd_bwd: workspace %zu < required %zu", workspace_bytes, L.total);
         return HICGAT_ERR_WORKSPACE;
@@ -460,14 +711,21 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     P.mpart = reinterpret_cast<double*>(ws + L.off_mpart);
     P.gpart = reinterpret_cast<float*>(ws + L.off_gpart);
     dim3 grid(L.nstrips, L.nchunks);
-    const size_t smem = (sizeof(float4) + sizeof(float2)) * (size_t)L.rb;
+    cudaError_t err = cudaSuccess;
     switch (mode) {
-#define HICGAT_CASE(M) case M: pairloss_kernel<M><<<grid, kThreads, smem, stream>>>(P); break;
-        HICGAT_CASE(0u) HICGAT_CASE(1u) HICGAT_CASE(2u) HICGAT_CASE(3u)
-        HICGAT_CASE(4u) HICGAT_CASE(5u) HICGAT_CASE(6u) HICGAT_CASE(7u)
+#define HICGAT_CASE(M) case M: err = launch_mode<M>(variant, map, P, grid, stream); break;
+        HICGAT_CASE(0u) HICGAT_CASE(1u) HICGAT_CASE(2u) HICGAT_CASE(3u) HICGAT_CASE(4u)
+        HICGAT_CASE(5u) HICGAT_CASE(6u) HICGAT_CASE(7u) HICGAT_CASE(8u) HICGAT_CASE(9u)
 #undef HICGAT_CASE
+        default:
+            set_error("hicgat_pairloss_fwd_bwd: unsupported mode 0x%x", mode);
+            return HICGAT_ERR_INVALID;
     }
-    HICGAT_CHECK_LAUNCH("pairloss_kernel");
+    if (err != cudaSuccess) {
+        set_error("pairloss kernel launch failed: %s", cudaGetErrorString(err));
+        return HICGAT_ERR_CUDA;
+    }
+    count_launch();
     return HICGAT_OK;
 }
 

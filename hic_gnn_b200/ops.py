@@ -11,7 +11,10 @@ from . import _native as N
 
 _MODES = {
     "mse": N.PAIR_GRAD_MSE,
-    "mse_moments": N.PAIR_GRAD_MSE | N.PAIR_MOMENTS,
+    # per-step training mode of the MSE + Pearson loop: only the coordinate-dependent statistics
+    # are accumulated; sum t / sum t^2 are constants of the target (WishTarget.t_moments)
+    "mse_moments": N.PAIR_GRAD_MSE | N.PAIR_MOMENTS_D,
+    "mse_moments_full": N.PAIR_GRAD_MSE | N.PAIR_MOMENTS,
     "contrastive": N.PAIR_GRAD_L1 | N.PAIR_MOMENTS,
     "moments": N.PAIR_MOMENTS,
     "value": 0,
@@ -72,6 +75,18 @@ class WishTarget:
     def dense(self) -> torch.Tensor:
         return self.data[:, : self.n]
 
+    def t_moments(self) -> torch.Tensor:
+        """f64[8] holding this row block's ``sum_{i<j} t`` and ``sum_{i<j} t^2`` in slots 4 and 5
+        (zeros elsewhere): the target-only Pearson moments, computed once by a full-moment launch
+        and added to the per-step ``HICGAT_PAIR_MOMENTS_D`` result."""
+        if getattr(self, "_tmom", None) is None:
+            zeros = torch.zeros(self.n, 3, dtype=torch.float32, device=self.data.device)
+            m, _ = pairloss_raw(zeros, self, N.PAIR_MOMENTS, 0.0, 0.0)
+            out = torch.zeros_like(m)
+            out[4:6] = m[4:6]
+            self._tmom = out
+        return self._tmom
+
 
 # ------------------------------------------------------------------------------ pair loss
 class _PairWorkspace:
@@ -129,6 +144,8 @@ class _PairLossFn(torch.autograd.Function):
             moments, grad = reducer(coords.detach())
         else:
             moments, grad = pairloss_raw(coords.detach(), target, mode, c_mse, c_l1)
+            if mode & N.PAIR_MOMENTS_D and not mode & N.PAIR_MOMENTS:
+                moments = moments + target.t_moments()
         ctx.save_for_backward(grad)
         ctx.mark_non_differentiable(moments)
         if mode_name == "contrastive":
@@ -150,7 +167,7 @@ def pairwise_loss(coords: torch.Tensor, target: WishTarget, mode: str = "mse", r
          ``"mse_moments"``  same + Pearson/L1 moments in one pass    HiC_GAT_generalize_directly.py:206-225
          ``"contrastive"``  0.1*mean_{i<j}|t-d| (f64)                train_and_test_same_res_GAT_node2vec.py:131-134
     """
-    if mode not in ("mse", "mse_moments", "contrastive"):
+    if mode not in ("mse", "mse_moments", "mse_moments_full", "contrastive"):
         raise ValueError(mode)
     return _PairLossFn.apply(coords, target, mode, reducer)
 
@@ -161,8 +178,12 @@ def sharded_reducer(target: WishTarget, mode: str, group=None):
 
     n = target.n
     npairs = n * (n - 1) / 2.0
-    fn = sharding.cuda_local_fn(target, _MODES[mode], 4.0 / (float(n) * float(n)), 0.1 / max(npairs, 1.0))
-    return sharding.ShardedPairLoss(n, fn, target.data.device, group)
+    m = _MODES[mode]
+    fn = sharding.cuda_local_fn(target, m, 4.0 / (float(n) * float(n)), 0.1 / max(npairs, 1.0))
+    const = None
+    if m & N.PAIR_MOMENTS_D and not m & N.PAIR_MOMENTS:
+        const = sharding.allreduce_packed(target.t_moments().clone(), group)  # global sum t, sum t^2: once
+    return sharding.ShardedPairLoss(n, fn, target.data.device, group, moment_const=const)
 
 
 def pair_moments(coords: torch.Tensor, target: WishTarget) -> torch.Tensor:

@@ -50,14 +50,18 @@ class ShardedPairLoss:
     ``local_fn(coords, packed)`` fills the packed buffer for the local block (the CUDA kernel
     in production; tests inject a CPU stand-in)."""
 
-    def __init__(self, n: int, local_fn, device, group=None):
+    def __init__(self, n: int, local_fn, device, group=None, moment_const=None):
         self.n, self.local_fn, self.group = n, local_fn, group
         self.packed = torch.zeros(N.PAIR_NMOM + 3 * n, dtype=torch.float64, device=device)
+        self.moment_const = moment_const  # f64[8] added after the reduction (target-only moments)
 
     def __call__(self, coords: torch.Tensor):
         self.local_fn(coords, self.packed)
         allreduce_packed(self.packed, self.group)
-        return unpack(self.packed, self.n)
+        moments, grad = unpack(self.packed, self.n)
+        if self.moment_const is not None:
+            moments = moments + self.moment_const
+        return moments, grad
 
 
 def cuda_local_fn(target, mode: int, c_mse: float, c_l1: float):

@@ -74,6 +74,11 @@ HICGAT_API uint64_t hicgat_launch_count(void);
 #define HICGAT_PAIR_GRAD_MSE 1u
 #define HICGAT_PAIR_GRAD_L1 2u
 #define HICGAT_PAIR_MOMENTS 4u
+/* Per-step subset for training with the MSE + Pearson loss: only the statistics that depend on
+ * the coordinates ([2] sum d, [3] sum d^2, [6] sum d t, [7] sum (d-t)^2; [1],[4],[5] are written
+ * as 0).  sum t and sum t^2 are constants of the target: take them ONCE from a
+ * HICGAT_PAIR_MOMENTS launch.  Implied by HICGAT_PAIR_MOMENTS. */
+#define HICGAT_PAIR_MOMENTS_D 8u
 #define HICGAT_PAIR_NMOM 8
 
 HICGAT_API size_t hicgat_pairloss_workspace_bytes(int64_t n, int64_t r0, int64_t r1);
@@ -88,7 +93,8 @@ HICGAT_API int hicgat_pairloss_fwd_bwd_packed(const float* coords, const float* 
                                    int64_t n, int64_t r0, int64_t r1, uint32_t mode, float c_mse,
                                    float c_l1, double* packed, void* workspace,
                                    size_t workspace_bytes, hicgat_stream_t stream);
-/* Tuning hook (bench/tests): rows per CTA row-chunk and kernel variant; 0 = library default. */
+/* Tuning hook (bench/tests): rows per CTA row-chunk (0 = library default) and kernel variant:
+ * 0 = TMA tile ring (cp.async.bulk.tensor + mbarrier, default), 1 = per-lane streaming loads. */
 HICGAT_API int hicgat_pairloss_set_tuning(int rows_per_cta, int variant);
 
 /* Materialising variant kept for API parity of model.forward() (returns the N x N matrix,

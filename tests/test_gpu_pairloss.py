@@ -75,11 +75,18 @@ def test_moments_match_scipy_and_contrastive(n):
     coords = random_coords(n, seed=2)
     dist_truth, dist_out = oloss.triu_pairs(truth, coords)
     want_r = pearsonr(dist_truth.numpy(), dist_out.numpy())[0]
-    got_l, got_g, m = _gpu_loss(coords, truth, "mse_moments")
     npairs = n * (n - 1) / 2
-    assert abs(float(pearson_from_moments(m, npairs)) - want_r) < 1e-6
     want_l, want_g = _oracle_mse(coords, truth)
+    # per-step training mode (coordinate-dependent moments from the kernel + cached target moments)
+    got_l, got_g, m_light = _gpu_loss(coords, truth, "mse_moments")
+    assert abs(float(pearson_from_moments(m_light, npairs)) - want_r) < 1e-6
     assert abs(float(got_l) - float(want_l)) / float(want_l) < TOL and rel_err(got_g, want_g) < TOL
+    # all moments in one pass
+    got_l, got_g, m = _gpu_loss(coords, truth, "mse_moments_full")
+    assert abs(float(pearson_from_moments(m, npairs)) - want_r) < 1e-6
+    assert abs(float(got_l) - float(want_l)) / float(want_l) < TOL and rel_err(got_g, want_g) < TOL
+    for k in (0, 2, 3, 4, 5, 6, 7):
+        assert abs(float(m_light[k]) - float(m[k])) <= 1e-6 * abs(float(m[k])), k
     # raw moments
     d, t = dist_out.double(), dist_truth.double()
     for k, want in [(1, (d - t).abs().sum()), (2, d.sum()), (3, (d * d).sum()), (4, t.sum()), (5, (t * t).sum()), (6, (d * t).sum()), (7, ((d - t) ** 2).sum())]:
@@ -100,7 +107,7 @@ def test_row_sharded_blocks_sum_to_full_and_are_deterministic():
     truth = wish_from_map(small_map(n, 0.4, seed=8), 1.0).cuda()
     coords = random_coords(n, seed=3).cuda()
     full = hg.WishTarget.from_dense(truth)
-    mode = ops._MODES["mse_moments"]
+    mode = ops._MODES["mse_moments_full"]
     m_full, g_full = ops.pairloss_raw(coords, full, mode, 4.0 / n**2, 0.0)
     m_full2, g_full2 = ops.pairloss_raw(coords, full, mode, 4.0 / n**2, 0.0)
     assert torch.equal(m_full, m_full2) and torch.equal(g_full, g_full2)  # bit-reproducible
@@ -116,6 +123,8 @@ def test_row_sharded_blocks_sum_to_full_and_are_deterministic():
 
 
 def test_tuning_variants_agree():
+    """Row-chunk sizes and the two load mechanisms (TMA tile ring / per-lane streaming loads)
+    compute the same sums, up to f32 partial-sum grouping."""
     import hic_gnn_b200 as hg
     from hic_gnn_b200 import _native as N
     from hic_gnn_b200 import ops
@@ -126,14 +135,50 @@ def test_tuning_variants_agree():
     tgt = hg.WishTarget.from_dense(truth)
     ref = None
     try:
-        for rb in (0, 8, 64, 256, 1024):
-            assert N.lib().hicgat_pairloss_set_tuning(rb, 0) == 0
-            m, g = ops.pairloss_raw(coords, tgt, ops._MODES["mse_moments"], 4.0 / n**2, 0.0)
-            if ref is None:
-                ref = (m.clone(), g.clone())
-            assert rel_err(m, ref[0]) < 1e-7 and rel_err(g, ref[1]) < 1e-5
+        for variant in (0, 1):
+            for rb in (0, 8, 64, 256, 1024):
+                assert N.lib().hicgat_pairloss_set_tuning(rb, variant) == 0
+                for mode in ("mse_moments_full", "contrastive"):
+                    m, g = ops.pairloss_raw(coords, tgt, ops._MODES[mode], 4.0 / n**2, 0.1 / (n * (n - 1) / 2))
+                    if ref is None:
+                        ref = {}
+                    if mode not in ref:
+                        ref[mode] = (m.clone(), g.clone())
+                    assert rel_err(m, ref[mode][0]) < 1e-7 and rel_err(g, ref[mode][1]) < 1e-5, (variant, rb, mode)
     finally:
         N.lib().hicgat_pairloss_set_tuning(0, 0)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,r0,r1", [(130, 0, 130), (777, 3, 500), (1000, 999, 1000), (513, 64, 449)])
+def test_row_blocks_any_alignment_both_variants(variant, n, r0, r1):
+    """Row blocks that start / end at rows that are not multiples of the tile height, single-row
+    blocks and blocks shorter than one tile, against an f64 torch evaluation of the same sums."""
+    import hic_gnn_b200 as hg
+    from hic_gnn_b200 import _native as N
+    from hic_gnn_b200 import ops
+
+    g = torch.Generator().manual_seed(n + r0)
+    truth = torch.rand(n, n, generator=g, dtype=torch.float64)
+    truth = (truth + truth.t()) / 2
+    truth.fill_diagonal_(0)
+    coords = random_coords(n, seed=r1)
+    c = coords.double()
+    d = torch.cdist(c[r0:r1], c)
+    t = truth[r0:r1].float().double()
+    e = d - t
+    up = torch.arange(r0, r1).unsqueeze(1) < torch.arange(n).unsqueeze(0)
+    want = torch.tensor([(e * e).sum(), e[up].abs().sum(), d[up].sum(), (d[up] ** 2).sum(), t[up].sum(), (t[up] ** 2).sum(), (d[up] * t[up]).sum(), (e[up] ** 2).sum()])
+    w = torch.where(d > 0, e / d.clamp(min=1e-30), torch.zeros_like(d))
+    gwant = (4.0 / n**2) * (w.unsqueeze(-1) * (c.unsqueeze(0) - c[r0:r1].unsqueeze(1))).sum(0)
+    try:
+        assert N.lib().hicgat_pairloss_set_tuning(0, variant) == 0
+        blk = hg.WishTarget.from_dense(truth.cuda(), r0, r1)
+        m, gr = ops.pairloss_raw(coords.cuda(), blk, ops._MODES["mse_moments_full"], 4.0 / n**2, 0.0)
+    finally:
+        N.lib().hicgat_pairloss_set_tuning(0, 0)
+    assert rel_err(m, want) < TOL
+    assert rel_err(gr, gwant) < TOL
 
 
 def test_pairdist_forward_backward_match_cdist():
