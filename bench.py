@@ -55,9 +55,11 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
-    ap.add_argument("--loss-mode", default="mse_moments", choices=["mse", "mse_moments", "contrastive"])
+    ap.add_argument("--loss-mode", default="mse_moments", choices=["mse", "mse_moments", "mse_moments_full", "contrastive"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--train-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--variant", type=int, default=0, help="pair-loss kernel: 0 = TMA tile ring (default), 1 = per-lane streaming loads")
+    ap.add_argument("--rows-per-cta", type=int, default=0, help="pair-loss row-chunk override (0 = library default)")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -320,6 +322,8 @@ def run_native(args):
     coords = (0.3 * torch.randn(n, 3, generator=g)).to(dev)
     nloc = r1 - r0
     mode = ops._MODES[args.loss_mode]
+    if args.variant or args.rows_per_cta:
+        N.set_pairloss_tuning(args.rows_per_cta, args.variant)
     c_mse, c_l1 = 4.0 / (float(n) * float(n)), 0.1 / (n * (n - 1) / 2.0)
     target_bytes = nloc * target.pitch * 4
     t_setup = time.time() - t_setup
@@ -445,7 +449,7 @@ def run_native(args):
                        "l2": f"no flush: each step streams {target_bytes / 1e6:.0f} MB of target per rank (L2 is 126 MB)",
                        "setup_s": round(t_setup, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "pairloss_kernel", "kernel_ms": kern_ms, "algorithmic_bytes": nloc * n * 4.0, "peak_source": peak_src,
+                         "kernel": "pairloss_tma_kernel" if args.variant == 0 else "pairloss_ldg_kernel", "kernel_ms": kern_ms, "algorithmic_bytes": nloc * n * 4.0, "peak_source": peak_src,
                          "frac_of_spec_8000": achieved / 8000.0},
             "cpu_baseline": cpu,
             "e2e": e2e,

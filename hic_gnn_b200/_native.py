@@ -77,3 +77,18 @@ def check(rc: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(lib().hicgat_launch_count())
+
+
+_tuning_epoch = 0
+
+
+def tuning_epoch() -> int:
+    return _tuning_epoch
+
+
+def set_pairloss_tuning(rows_per_cta: int = 0, variant: int = 0) -> None:
+    """``hicgat_pairloss_set_tuning`` + invalidation of the cached workspaces (their size depends
+    on the row-chunk length).  ``variant`` 0 = TMA tile ring, 1 = per-lane streaming loads."""
+    global _tuning_epoch
+    check(lib().hicgat_pairloss_set_tuning(rows_per_cta, variant), "hicgat_pairloss_set_tuning")
+    _tuning_epoch += 1

@@ -90,14 +90,17 @@ class WishTarget:
 
 # ------------------------------------------------------------------------------ pair loss
 class _PairWorkspace:
+    """Per (device, n, row block) scratch for the cross-CTA reductions, re-sized when the kernel
+    tuning changes (``_native.set_pairloss_tuning`` bumps the epoch)."""
+
     _cache: dict = {}
 
     @classmethod
     def get(cls, device, n, r0, r1):
-        key = (device.index, n, r0, r1)
+        key = (device.index, n, r0, r1, N.tuning_epoch())
         ws = cls._cache.get(key)
-        need = N.lib().hicgat_pairloss_workspace_bytes(n, r0, r1)
-        if ws is None or ws.numel() < need:
+        if ws is None:
+            need = N.lib().hicgat_pairloss_workspace_bytes(n, r0, r1)
             ws = torch.empty(need, dtype=torch.uint8, device=device)
             cls._cache[key] = ws
         return ws

@@ -137,7 +137,7 @@ def test_tuning_variants_agree():
     try:
         for variant in (0, 1):
             for rb in (0, 8, 64, 256, 1024):
-                assert N.lib().hicgat_pairloss_set_tuning(rb, variant) == 0
+                N.set_pairloss_tuning(rb, variant)
                 for mode in ("mse_moments_full", "contrastive"):
                     m, g = ops.pairloss_raw(coords, tgt, ops._MODES[mode], 4.0 / n**2, 0.1 / (n * (n - 1) / 2))
                     if ref is None:
@@ -146,7 +146,7 @@ def test_tuning_variants_agree():
                         ref[mode] = (m.clone(), g.clone())
                     assert rel_err(m, ref[mode][0]) < 1e-7 and rel_err(g, ref[mode][1]) < 1e-5, (variant, rb, mode)
     finally:
-        N.lib().hicgat_pairloss_set_tuning(0, 0)
+        N.set_pairloss_tuning(0, 0)
 
 
 @pytest.mark.parametrize("variant", [0, 1])
@@ -172,11 +172,11 @@ def test_row_blocks_any_alignment_both_variants(variant, n, r0, r1):
     w = torch.where(d > 0, e / d.clamp(min=1e-30), torch.zeros_like(d))
     gwant = (4.0 / n**2) * (w.unsqueeze(-1) * (c.unsqueeze(0) - c[r0:r1].unsqueeze(1))).sum(0)
     try:
-        assert N.lib().hicgat_pairloss_set_tuning(0, variant) == 0
+        N.set_pairloss_tuning(0, variant)
         blk = hg.WishTarget.from_dense(truth.cuda(), r0, r1)
         m, gr = ops.pairloss_raw(coords.cuda(), blk, ops._MODES["mse_moments_full"], 4.0 / n**2, 0.0)
     finally:
-        N.lib().hicgat_pairloss_set_tuning(0, 0)
+        N.set_pairloss_tuning(0, 0)
     assert rel_err(m, want) < TOL
     assert rel_err(gr, gwant) < TOL
 
