@@ -566,12 +566,17 @@ int g_variant = 0;  // 0 = TMA ring (default), 1 = per-lane streaming loads
 int pick_rows_per_cta(int64_t nrows, int nstrips, int variant) {
     if (g_rows_per_cta > 0) return variant == 0 ? (g_rows_per_cta + kTileRows - 1) / kTileRows * kTileRows : g_rows_per_cta;
     if (variant == 0) {
-        // long row chunks amortise the ring fill (3 tiles) and the per-CTA combine; keep >= 4 waves
-        // of 2 CTAs x 148 SMs so the tail stays short
-        const int64_t want = 148 * 2 * 4;
-        int rb = 4096;
-        while (rb > kTileRows && (int64_t)nstrips * ((nrows + rb - 1) / rb) < want) rb >>= 1;
-        return rb;
+        // Makespan model: streaming time ~ total rows / (2 CTAs x 148 SMs) + a tail of about one
+        // chunk + a per-CTA cost (ring fill, combine) worth ~80 rows.  Minimising over the chunk
+        // length gives rb ~ sqrt(80 * nstrips * nrows / 296); chunks are then equalised so that no
+        // CTA is left with a sliver.
+        const double opt = sqrt(80.0 * (double)nstrips * (double)nrows / 296.0);
+        int64_t rb = ((int64_t)opt + kTileRows - 1) / kTileRows * kTileRows;
+        if (rb < kTileRows) rb = kTileRows;
+        if (rb > 4096) rb = 4096;
+        const int64_t nchunks = (nrows + rb - 1) / rb;
+        rb = ((nrows + nchunks - 1) / nchunks + kTileRows - 1) / kTileRows * kTileRows;
+        return (int)rb;
     }
     // largest chunk that still gives >= ~6 CTAs per SM (148 SMs); bounds the partial buffers
     const int64_t want = 148 * 6;

@@ -175,8 +175,9 @@ def pairwise_loss(coords: torch.Tensor, target: WishTarget, mode: str = "mse", r
     return _PairLossFn.apply(coords, target, mode, reducer)
 
 
-def sharded_reducer(target: WishTarget, mode: str, group=None):
-    """``reducer`` for :func:`pairwise_loss` when ``target`` is this rank's row block."""
+def sharded_reducer(target: WishTarget, mode: str, group=None, transport: str = "auto"):
+    """``reducer`` for :func:`pairwise_loss` when ``target`` is this rank's row block.
+    ``transport``: see :func:`sharding.make_sharded_pair_loss`."""
     from . import sharding
 
     n = target.n
@@ -186,7 +187,7 @@ def sharded_reducer(target: WishTarget, mode: str, group=None):
     const = None
     if m & N.PAIR_MOMENTS_D and not m & N.PAIR_MOMENTS:
         const = sharding.allreduce_packed(target.t_moments().clone(), group)  # global sum t, sum t^2: once
-    return sharding.ShardedPairLoss(n, fn, target.data.device, group, moment_const=const)
+    return sharding.make_sharded_pair_loss(n, fn, target.data.device, group, moment_const=const, transport=transport)
 
 
 def pair_moments(coords: torch.Tensor, target: WishTarget) -> torch.Tensor:

@@ -64,6 +64,71 @@ class ShardedPairLoss:
         return moments, grad
 
 
+class P2PShardedPairLoss:
+    """Same contract as :class:`ShardedPairLoss`, but the exchange is the hand-written one-shot
+    all-reduce over NVLink peer memory (``hicgat_allreduce_packed_p2p``): the fused loss kernel
+    writes its packed partial into a symmetric buffer that every rank maps, then ONE kernel per
+    rank does barrier + rank-ordered sum + unpack.  Two buffer halves alternate by step parity
+    (see csrc/comm.cu for why that makes a trailing barrier unnecessary)."""
+
+    SLOT_BASE = 256  # uint32 slot offset inside torch's signal pad (its own barriers use the low channels)
+
+    def __init__(self, n: int, local_fn, device, group=None, moment_const=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        self.n, self.local_fn = n, local_fn
+        self.count = N.PAIR_NMOM + 3 * n
+        self.half = (self.count + 1) // 2 * 2  # keeps the second half 16-byte aligned
+        self.buf = symm.empty(2 * self.half, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.world, self.rank = self.hdl.world_size, self.hdl.rank
+        if self.hdl.signal_pad_size < 4 * (self.SLOT_BASE + self.world):
+            raise RuntimeError("symmetric-memory signal pad too small")
+        self._bufs = (C.c_uint64 * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        self._pads = (C.c_uint64 * self.world)(*[int(p) for p in self.hdl.signal_pad_ptrs])
+        self.moment_const = moment_const
+        self.out_m = [torch.empty(N.PAIR_NMOM, dtype=torch.float64, device=device) for _ in range(2)]
+        self.out_g = [torch.empty(n, 3, dtype=torch.float32, device=device) for _ in range(2)]
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's buffer is zeroed and mapped before the first signal
+
+    def __call__(self, coords: torch.Tensor):
+        self.epoch += 1
+        par = self.epoch & 1
+        packed = self.buf[par * self.half: par * self.half + self.count]
+        self.local_fn(coords, packed)
+        m, g = self.out_m[par], self.out_g[par]
+        rc = N.lib().hicgat_allreduce_packed_p2p(
+            self._bufs, self._pads, self.rank, self.world, self.n, par * self.half * 8, self.SLOT_BASE, self.epoch & 0xFFFFFFFF,
+            None if self.moment_const is None else self.moment_const.data_ptr(), m.data_ptr(), g.data_ptr(),
+            torch.cuda.current_stream().cuda_stream,
+        )
+        N.check(rc, "hicgat_allreduce_packed_p2p")
+        return m, g
+
+
+def make_sharded_pair_loss(n: int, local_fn, device, group=None, moment_const=None, transport: str = "auto"):
+    """``transport``: ``"p2p"`` (one-shot kernel over NVLink peer memory), ``"nccl"`` (packed
+    ``all_reduce``) or ``"auto"`` (p2p on CUDA with an initialised multi-rank NCCL group when the
+    symmetric-memory rendezvous succeeds, else nccl)."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if transport == "p2p" or (transport == "auto" and multi and torch.device(device).type == "cuda"):
+        try:
+            return P2PShardedPairLoss(n, local_fn, device, group, moment_const)
+        except Exception as e:  # no symmetric memory on this system: the NCCL exchange is equivalent
+            if transport == "p2p":
+                raise
+            import warnings
+
+            warnings.warn(f"symmetric-memory exchange unavailable ({e!r}); using the NCCL all-reduce")
+    return ShardedPairLoss(n, local_fn, device, group, moment_const)
+
+
 def cuda_local_fn(target, mode: int, c_mse: float, c_l1: float):
     """The production ``local_fn``: hicgat_pairloss_fwd_bwd_packed on this rank's WishTarget."""
     from .ops import _PairWorkspace, _cuda, _stream

@@ -97,6 +97,23 @@ HICGAT_API int hicgat_pairloss_fwd_bwd_packed(const float* coords, const float* 
  * 0 = TMA tile ring (cp.async.bulk.tensor + mbarrier, default), 1 = per-lane streaming loads. */
 HICGAT_API int hicgat_pairloss_set_tuning(int rows_per_cta, int variant);
 
+/* ------------------------------------------------------------------------------------
+ * (3) Exchange step of the row-sharded loss: one-shot all-reduce of every rank's
+ * packed f64[8 + 3n] partial over NVLink peer memory (no counterpart in the reference, which is
+ * single-process).  Each rank's packed buffer lives in a SYMMETRIC
+ * allocation mapped by all ranks; `peer_bufs_host[r]` / `signal_pads_host[r]` are HOST arrays of
+ * the device addresses of rank r's buffer and signal pad in THIS process's address space.
+ * The kernel signals epoch `epoch` to all peers (uint32 slots `slot_base + rank` of their pads),
+ * waits for all peers, sums the partials at `buf_offset_bytes` in rank order (bit-identical on
+ * every rank) and writes moments f64[8] (+ `moment_const` if not NULL) and grad f32[n,3].
+ * Callers alternate two buffer halves by epoch parity and increase `epoch` by one per call,
+ * starting at 1 (pads zero-initialised); no other synchronisation is needed.
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API int hicgat_allreduce_packed_p2p(const uint64_t* peer_bufs_host, const uint64_t* signal_pads_host, int rank,
+                                int world, int64_t n, int64_t buf_offset_bytes, int slot_base, uint32_t epoch,
+                                const double* moment_const, double* out_moments, float* out_grad,
+                                hicgat_stream_t stream);
+
 /* Materialising variant kept for API parity of model.forward() (returns the N x N matrix,
  * models.py:39): dist[i,j] = |x_i - x_j|, and its backward
  * grad_coords[i] = sum_j (G[i,j] + G[j,i]) (x_i - x_j)/d_ij  (ATen _euclidean_dist_backward). */

@@ -27,8 +27,12 @@ def _worker(rank, world, port, n, tmpdir):
         _, tgt = ops.cont2dist(adj[r0:r1].contiguous(), 1.0, want_f64=False, want_f32=True, r0=r0, r1=r1, max_reduce=sharding.allreduce_max_)
         _, full = ops.cont2dist(adj, 1.0, want_f64=False, want_f32=True)
         assert torch.equal(tgt.dense(), full.dense()[r0:r1])
-        for mode in ("mse", "mse_moments", "contrastive"):
-            red = ops.sharded_reducer(tgt, mode)
+        for mode, transport in [("mse", "nccl"), ("mse_moments", "nccl"), ("contrastive", "nccl"),
+                                ("mse", "p2p"), ("mse_moments", "p2p"), ("contrastive", "p2p")]:
+            red = ops.sharded_reducer(tgt, mode, transport=transport)
+            if transport == "p2p":  # several steps: exercises the epoch / buffer-parity protocol
+                for _ in range(5):
+                    hg.pairwise_loss(coords, tgt, mode, reducer=red)
             loss_s, mom_s = hg.pairwise_loss(coords, tgt, mode, reducer=red)
             (g_s,) = torch.autograd.grad(loss_s, coords)
             loss_1, mom_1 = hg.pairwise_loss(coords, full, mode)
