@@ -565,6 +565,7 @@ int g_variant = 0;  // 0 = TMA ring (default), 1 = per-lane streaming loads
 
 int pick_rows_per_cta(int64_t nrows, int nstrips, int variant) {
     if (g_rows_per_cta > 0) return variant == 0 ? (g_rows_per_cta + kTileRows - 1) / kTileRows * kTileRows : g_rows_per_cta;
+    if (nrows <= 0) return kTileRows;  // empty row block: nothing is launched
     if (variant == 0) {
         // Makespan model: streaming time ~ total rows / (2 CTAs x 148 SMs) + a tail of about one
         // chunk + a per-CTA cost (ring fill, combine) worth ~80 rows.  Minimising over the chunk

@@ -262,7 +262,9 @@ def test_per_step_loss_and_gradients_along_oracle_trajectory(cls, mode, n, densi
         # step's gradients are not compared; the loss still is
         strict = watch.gap > 5e-7
         strict_steps += strict
-        _loss_f64(coords_o, truth, mode).backward()
+        lo64 = _loss_f64(coords_o, truth, mode)
+        lo64.backward()
+        lo64 = float(lo64.detach())
         g64 = _param_grads(om)
         # the reference's own f32 evaluation (this is what drives the oracle trajectory)
         opt.zero_grad()
@@ -272,7 +274,11 @@ def test_per_step_loss_and_gradients_along_oracle_trajectory(cls, mode, n, densi
         gm.zero_grad(set_to_none=True)
         lg, total, moments = gtrain.step_loss(gm, gdata.x.float(), gdata.edge_index, target, mode)
         lg.backward()
-        assert abs(float(lg.detach()) - float(lo.detach())) / abs(float(lo.detach())) < TOL, (s, float(lg.detach()), float(lo.detach()))
+        # loss value: 1e-5 against the f64 value of the reference formula; the reference's own f32
+        # evaluation (matmul-form cdist) sits within a few 1e-5 of that late in training
+        lgv, lov = float(lg.detach()), float(lo.detach())
+        assert abs(lgv - lo64) / abs(lo64) < TOL, (s, lgv, lo64)
+        assert abs(lgv - lov) / abs(lov) < max(TOL, 2 * abs(lov - lo64) / abs(lo64)), (s, lgv, lov, lo64)
         if mode == "mse_pearson":  # total = mse + alpha (1 - r), HiC_GAT_generalize_directly.py:219-225
             want_total, _, r, _ = oloss.mse_pearson_loss(coords_o.detach(), truth)
             assert abs(float(total) - float(want_total)) / abs(float(want_total)) < TOL
