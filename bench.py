@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="pair-loss kernel: 0 = TMA tile ring (default), 1 = per-lane streaming loads")
     ap.add_argument("--rows-per-cta", type=int, default=0, help="pair-loss row-chunk override (0 = library default)")
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"], help="exchange of the sharded loss partials")
+    ap.add_argument("--emulate-world", type=int, default=0, help="profiling aid: on ONE GPU run rank 0's row block of a W-way split (not a bench line)")
+    ap.add_argument("--no-measure-copy", dest="measure_copy", action="store_false", help="skip the same-process copy-bandwidth control")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -304,6 +306,8 @@ def run_native(args):
     # ---- inputs (outside every timed region): contact map -> CSR graph + this rank's target rows
     adj = synth.synthetic_map_chunked(n, density, device=dev)
     r0, r1 = sharding.row_block(n, rank, world)
+    if args.emulate_world and world == 1:
+        r0, r1 = sharding.row_block(n, 0, args.emulate_world)
     _, target = ops.cont2dist(adj[r0:r1], 1.0, want_f64=False, want_f32=True, r0=r0, r1=r1, max_reduce=sharding.allreduce_max_)
     want_train = not args.no_train
     graph = None
@@ -328,6 +332,24 @@ def run_native(args):
     c_mse, c_l1 = 4.0 / (float(n) * float(n)), 0.1 / (n * (n - 1) / 2.0)
     target_bytes = nloc * target.pitch * 4
     t_setup = time.time() - t_setup
+
+    # ---- (0) this box's copy bandwidth right now (same recipe as MEASURED_PEAKS.json: b.copy_(a), bytes read +
+    # written, best of 10): a same-process control for box-to-box variation, reported beside the roofline
+    copy_gbs = None
+    if args.measure_copy:
+        a_ = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+        b_ = torch.empty_like(a_)
+        best = float("inf")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(12):
+            e0.record()
+            b_.copy_(a_)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        copy_gbs = 2 * a_.numel() * 2 / (best * 1e-3) / 1e9
+        del a_, b_
+        torch.cuda.empty_cache()
 
     # ---- (1) resident loss step: fused kernel on the local rows + one packed all-reduce + unpack
     raw_local_fn = sharding.cuda_local_fn(target, mode, c_mse, c_l1)
@@ -452,12 +474,13 @@ def run_native(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "n_loci": n, "density": density, "pairs_per_step": float(n) * float(n), "loss_mode": args.loss_mode,
-                       "parallelism": f"rows{world}" if world > 1 else "single", "rows_per_rank": nloc, "exchange": transport,
+                       "parallelism": f"rows{world}" if world > 1 else ("single" if not args.emulate_world else f"rank0-of-{args.emulate_world} (emulated, NOT a bench line)"), "rows_per_rank": nloc, "exchange": transport,
                        "l2": f"no flush: each step streams {target_bytes / 1e6:.0f} MB of target per rank (L2 is 126 MB)",
                        "setup_s": round(t_setup, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "pairloss_tma_kernel" if args.variant == 0 else "pairloss_ldg_kernel", "kernel_ms": kern_ms, "algorithmic_bytes": nloc * n * 4.0, "peak_source": peak_src,
-                         "frac_of_spec_8000": achieved / 8000.0},
+                         "frac_of_spec_8000": achieved / 8000.0,
+                         "copy_gbs_this_run": copy_gbs, "frac_of_copy_this_run": (achieved / copy_gbs) if copy_gbs else None},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "train": train_out,

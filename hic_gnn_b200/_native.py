@@ -10,7 +10,8 @@ import os
 import re
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libhicgat_sm100.so")
+# HICGAT_LIB: A/B another build of the same ABI (kernel experiments); default = the in-tree library
+LIB_PATH = os.environ.get("HICGAT_LIB") or os.path.join(_PKG, "libhicgat_sm100.so")
 HEADER = os.path.join(os.path.dirname(_PKG), "include", "hicgat.h")
 
 _p, _i64, _i32, _u32, _f32, _f64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_float, C.c_double, C.c_size_t

@@ -33,6 +33,7 @@ constexpr int kThreads = kWarps * 32;     // variant 1 block size
 constexpr int kCols = 128;                // columns per CTA strip (32 lanes x 4)
 constexpr int kU = 8;                     // rows per warp per group / tile
 constexpr int kNM = HICGAT_PAIR_NMOM;
+constexpr int kCtaSlots = 148 * 2;        // resident CTAs of the TMA kernel (2 per SM)
 constexpr int kTileRows = kWarps * kU;    // 64 rows per CTA tile step (8 per warp)
 constexpr int kStages = 3;                // TMA slots per warp
 constexpr int kSubTileBytes = kU * kCols * 4;               // 4096: one warp's 8 rows x 128 columns
@@ -166,6 +167,7 @@ struct Params {
     double* grad64;        // optional f64 copy of grad (packed all-reduce buffer)
     float* gpart;          // [nchunks][nstrips][384]
     double* mpart;         // [nchunks*nstrips][kNM]
+    double* spart;         // [nstrips][kNM] per-strip moment partials
     unsigned* strip_count; // [nstrips]
     unsigned* done_count;  // [1]
 };
@@ -192,16 +194,27 @@ __device__ __forceinline__ void load_columns(ColumnRegs& c, const float* __restr
 }
 
 // kU rows of one warp: t[u] = the lane's 4 target values of row (rg + u); xi from shared memory.
-template <uint32_t MODE>
-__device__ __forceinline__ void process_group(Acc& a, const ColumnRegs& c, const float4 (&t)[kU], const float4* __restrict__ s_xy,
-                                              const float2* __restrict__ s_z, int rows_here, int rg, int col0, int n, bool edge,
+struct XiPtr {  // x_i rows behind ordinary shared-memory pointers (variant 1)
+    const float4* xy;
+    const float2* z;
+    __device__ __forceinline__ void load(int u, float4& oxy, float2& oz) const { oxy = xy[u]; oz = z[u]; }
+};
+struct XiAddr {  // x_i rows behind 32-bit shared-space addresses (TMA variant)
+    uint32_t xy, z;
+    __device__ __forceinline__ void load(int u, float4& oxy, float2& oz) const;
+};
+
+template <uint32_t MODE, typename XI>
+__device__ __forceinline__ void process_group(Acc& a, const ColumnRegs& c, const float4 (&t)[kU], const XI xi,
+                                              int rows_here, int rg, int col0, int n, bool edge,
                                               int strip_lo, int strip_hi, float c_mse, float c_l1) {
     const bool fast = !edge && rows_here == kU;
     if (fast && rg + kU - 1 < strip_lo) {  // strictly above the diagonal
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            float4 xy = s_xy[u];
-            float2 zz = s_z[u];
+            float4 xy;
+            float2 zz;
+            xi.load(u, xy, zz);
             f2 xix = f2_pack(xy.x, xy.y), xiy = f2_pack(xy.z, xy.w), xiz = f2_pack(zz.x, zz.y);
             pair_fast<MODE, true>(a, 0, c.xjx[0], c.xjy[0], c.xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), c_mse, c_l1);
             pair_fast<MODE, true>(a, 1, c.xjx[1], c.xjy[1], c.xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), c_mse, c_l1);
@@ -209,8 +222,9 @@ __device__ __forceinline__ void process_group(Acc& a, const ColumnRegs& c, const
     } else if (fast && rg > strip_hi) {    // strictly below
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            float4 xy = s_xy[u];
-            float2 zz = s_z[u];
+            float4 xy;
+            float2 zz;
+            xi.load(u, xy, zz);
             f2 xix = f2_pack(xy.x, xy.y), xiy = f2_pack(xy.z, xy.w), xiz = f2_pack(zz.x, zz.y);
             pair_fast<MODE, false>(a, 0, c.xjx[0], c.xjy[0], c.xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), c_mse, c_l1);
             pair_fast<MODE, false>(a, 1, c.xjx[1], c.xjy[1], c.xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), c_mse, c_l1);
@@ -220,8 +234,9 @@ __device__ __forceinline__ void process_group(Acc& a, const ColumnRegs& c, const
         for (int u = 0; u < kU; ++u) {
             if (u < rows_here) {
                 const int r = rg + u;
-                float4 xy = s_xy[u];
-                float2 zz = s_z[u];
+                float4 xy;
+                float2 zz;
+                xi.load(u, xy, zz);
                 f2 xix = f2_pack(xy.x, xy.y), xiy = f2_pack(xy.z, xy.w), xiz = f2_pack(zz.x, zz.y);
                 f2 mu0 = f2_pack((col0 + 0 < n && r < col0 + 0) ? 1.f : 0.f, (col0 + 1 < n && r < col0 + 1) ? 1.f : 0.f);
                 f2 mu1 = f2_pack((col0 + 2 < n && r < col0 + 2) ? 1.f : 0.f, (col0 + 3 < n && r < col0 + 3) ? 1.f : 0.f);
@@ -301,60 +316,58 @@ __device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int 
         for (int w = 0; w < kWarps; ++w) s += S.m[w][tid];
         __stcg(P.mpart + (size_t)cta * kNM + tid, s);
     }
-    __threadfence();
+    // Publish: the block barrier orders every thread's partial stores before thread 0's fence,
+    // and the fence is cumulative, so ONE membar per CTA suffices (a per-thread __threadfence()
+    // costs every warp a memory barrier on the critical path of the CTA's epilogue).
     __syncthreads();
     if (tid == 0) {
+        __threadfence();
         S.ticket[0] = atomicAdd(P.strip_count + strip, 1u);
-        S.ticket[1] = atomicAdd(P.done_count, 1u);
+        __threadfence();  // acquire side for the last CTA of the strip
     }
     __syncthreads();
-    const bool last_in_strip = S.ticket[0] == (unsigned)(P.nchunks - 1);
-    const bool last_overall = S.ticket[1] == (unsigned)(P.nchunks * P.nstrips - 1);
-    if (!last_in_strip && !last_overall) return;
-    __threadfence();
+    if (S.ticket[0] != (unsigned)(P.nchunks - 1)) return;
+    // ---- last CTA of this column strip: add the strip's row-chunk partials in chunk order
     if constexpr ((MODE & 3u) != 0) {
-        if (last_in_strip) {
-            const float scale = ((MODE & 3u) == HICGAT_PAIR_GRAD_MSE) ? P.c_mse
-                                : ((MODE & 3u) == HICGAT_PAIR_GRAD_L1) ? P.c_l1 : 1.f;
-            for (int i = tid; i < kCols * 3; i += nthreads) {
-                double s = 0.0;
-                for (int c = 0; c < P.nchunks; ++c)
-                    s += (double)__ldcg(P.gpart + ((size_t)c * P.nstrips + strip) * (kCols * 3) + i);
-                const int col = strip * kCols + i / 3;
-                if (col < n) {
-                    const double v = s * (double)scale;
-                    if (P.grad) P.grad[(size_t)strip * kCols * 3 + i] = (float)v;
-                    if (P.grad64) P.grad64[(size_t)strip * kCols * 3 + i] = (double)(float)v;
-                }
+        const float scale = ((MODE & 3u) == HICGAT_PAIR_GRAD_MSE) ? P.c_mse
+                            : ((MODE & 3u) == HICGAT_PAIR_GRAD_L1) ? P.c_l1 : 1.f;
+        for (int i = tid; i < kCols * 3; i += nthreads) {
+            const float* src = P.gpart + (size_t)strip * (kCols * 3) + i;
+            const size_t stride = (size_t)P.nstrips * (kCols * 3);
+            double s = 0.0;
+            int c = 0;
+            for (; c + 4 <= P.nchunks; c += 4) {  // 4 independent loads in flight, summed in chunk order
+                const float v0 = __ldcg(src + (size_t)c * stride), v1 = __ldcg(src + (size_t)(c + 1) * stride);
+                const float v2 = __ldcg(src + (size_t)(c + 2) * stride), v3 = __ldcg(src + (size_t)(c + 3) * stride);
+                s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+            }
+            for (; c < P.nchunks; ++c) s += (double)__ldcg(src + (size_t)c * stride);
+            const int col = strip * kCols + i / 3;
+            if (col < n) {
+                const double v = s * (double)scale;
+                if (P.grad) P.grad[(size_t)strip * kCols * 3 + i] = (float)v;
+                if (P.grad64) P.grad64[(size_t)strip * kCols * 3 + i] = (double)(float)v;
             }
         }
     }
-    if (last_overall) {
-        // fixed-order f64 reduction of all CTA moment partials (S.m is free again: every thread
-        // passed the barrier above after reading it)
-        double m[kNM];
-#pragma unroll
-        for (int k = 0; k < kNM; ++k) m[k] = 0.0;
-        const int total = P.nchunks * P.nstrips;
-        if (tid < kThreads) {
-            for (int c = tid; c < total; c += kThreads) {
-#pragma unroll
-                for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.mpart + (size_t)c * kNM + k);
-            }
-#pragma unroll
-            for (int k = 0; k < kNM; ++k) m[k] = warp_sum(m[k]);
-            if ((tid & 31) == 0) {
-#pragma unroll
-                for (int k = 0; k < kNM; ++k) S.m[tid >> 5][k] = m[k];
-            }
-        }
-        __syncthreads();
-        if (tid < kNM) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) s += S.m[w][tid];
-            P.moments[tid] = s;
-        }
+    if (tid < kNM) {  // the strip's moments -> one partial per strip
+        double s = 0.0;
+        for (int c = 0; c < P.nchunks; ++c) s += __ldcg(P.mpart + ((size_t)c * P.nstrips + strip) * kNM + tid);
+        __stcg(P.spart + (size_t)strip * kNM + tid, s);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        S.ticket[1] = atomicAdd(P.done_count, 1u);
+        __threadfence();
+    }
+    __syncthreads();
+    if (S.ticket[1] != (unsigned)(P.nstrips - 1)) return;
+    // ---- last strip to finish: fixed-order f64 reduction of the per-strip moment partials
+    if (tid < kNM) {
+        double s = 0.0;
+        for (int st = 0; st < P.nstrips; ++st) s += __ldcg(P.spart + (size_t)st * kNM + tid);
+        P.moments[tid] = s;
     }
 }
 
@@ -405,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_ldg_kernel(const Params 
                 t[u] = (u < rows_here && can_load) ? ldg_stream_f4(tbase + (size_t)(rl + u) * P.pitch)
                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        process_group<MODE>(a, c, t, s_xy + rl, s_z + rl, rows_here, row_begin + rl, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1);
+        process_group<MODE>(a, c, t, XiPtr{s_xy + rl, s_z + rl}, rows_here, row_begin + rl, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1);
     }
     park_warp<MODE>(a, S, warp, lane);
     __syncthreads();
@@ -432,6 +445,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+// explicit shared-space accesses: the ring pointer went through an integer round trip (128-byte
+// alignment), so plain C++ dereferences would compile to generic LD/ST with 64-bit address math
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t addr, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void XiAddr::load(int u, float4& oxy, float2& oz) const {
+    oxy = lds_f4(xy + u * 16);
+    oz = lds_f2(z + u * 8);
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
@@ -476,13 +508,10 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_tma_kernel(const __grid_
         const int gr = min(row_begin + t * kTileRows + wrow + xi_row, n - 1);
         return lane < 24 ? __ldg(P.coords + (size_t)gr * 3 + xi_comp) : 0.f;
     };
+    const uint32_t wring_s = smem_u32(wring);
+    const uint32_t xi_off = kSubTileBytes + (xi_comp < 2 ? xi_row * 16 + xi_comp * 8 : kU * 16 + xi_row * 8);
     auto xi_store = [&](int s, float v) {
-        if (lane < 24) {
-            unsigned char* slot = wring + (size_t)s * kSlotBytes + kSubTileBytes;
-            float2* dst = xi_comp < 2 ? reinterpret_cast<float2*>(slot + xi_row * 16 + xi_comp * 8)
-                                      : reinterpret_cast<float2*>(slot + kU * 16 + xi_row * 8);
-            *dst = make_float2(v, v);
-        }
+        if (lane < 24) sts_f2(wring_s + s * kSlotBytes + xi_off, v, v);
     };
     auto issue = [&](int t, int s) {  // lane 0 only
         mbar_arrive_expect_tx(&full_bar[warp][s], (uint32_t)kSubTileBytes);
@@ -506,15 +535,13 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_tma_kernel(const __grid_
         const bool refill = t + kStages < ntiles;
         const float xi_next = refill ? xi_fetch(t + kStages) : 0.f;   // in flight during the compute below
         mbar_wait(&full_bar[warp][s], (uint32_t)(use & 1));
-        const unsigned char* slot = wring + (size_t)s * kSlotBytes;
-        const float4* tile = reinterpret_cast<const float4*>(slot);
-        const float4* s_xy = reinterpret_cast<const float4*>(slot + kSubTileBytes);
-        const float2* s_z = reinterpret_cast<const float2*>(slot + kSubTileBytes + kU * 16);
+        const uint32_t slot = wring_s + s * kSlotBytes;
+        const XiAddr xi{slot + kSubTileBytes, slot + kSubTileBytes + kU * 16};
         const int rows_here = max(0, min(kU, nrows - (t * kTileRows + wrow)));
         float4 tv[kU];
 #pragma unroll
-        for (int u = 0; u < kU; ++u) tv[u] = tile[u * (kCols / 4) + lane];
-        process_group<MODE>(a, c, tv, s_xy, s_z, rows_here, row_begin + t * kTileRows + wrow, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1);
+        for (int u = 0; u < kU; ++u) tv[u] = lds_f4(slot + lane * 16 + u * (kCols * 4));
+        process_group<MODE>(a, c, tv, xi, rows_here, row_begin + t * kTileRows + wrow, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1);
         __syncwarp();  // every lane is done with slot s
         if (refill) {
             if (lane == 0) issue(t + kStages, s);
@@ -567,17 +594,30 @@ int pick_rows_per_cta(int64_t nrows, int nstrips, int variant) {
     if (g_rows_per_cta > 0) return variant == 0 ? (g_rows_per_cta + kTileRows - 1) / kTileRows * kTileRows : g_rows_per_cta;
     if (nrows <= 0) return kTileRows;  // empty row block: nothing is launched
     if (variant == 0) {
-        // Makespan model: streaming time ~ total rows / (2 CTAs x 148 SMs) + a tail of about one
-        // chunk + a per-CTA cost (ring fill, combine) worth ~80 rows.  Minimising over the chunk
-        // length gives rb ~ sqrt(80 * nstrips * nrows / 296); chunks are then equalised so that no
-        // CTA is left with a sliver.
-        const double opt = sqrt(80.0 * (double)nstrips * (double)nrows / 296.0);
-        int64_t rb = ((int64_t)opt + kTileRows - 1) / kTileRows * kTileRows;
-        if (rb < kTileRows) rb = kTileRows;
-        if (rb > 4096) rb = 4096;
-        const int64_t nchunks = (nrows + rb - 1) / rb;
-        rb = ((nrows + nchunks - 1) / nchunks + kTileRows - 1) / kTileRows * kTileRows;
-        return (int)rb;
+        // One CTA per (column strip, row chunk) item, 2 resident CTAs per SM.  Long chunks keep the
+        // per-CTA prologue / combine and the partial buffers small; what matters then is the wave
+        // quantisation ceil(items / 296) / (items / 296).  Among chunk lengths of 1024..4096 rows
+        // (shorter only when the block would otherwise give fewer than two items per CTA slot)
+        // pick the one with the smallest makespan estimate, preferring longer chunks on ties.
+        int64_t nch_lo = (nrows + 4095) / 4096, nch_hi = nrows / 1024;
+        int64_t nch_items = (2 * kCtaSlots + nstrips - 1) / nstrips;
+        if (nch_items > (nrows + kTileRows - 1) / kTileRows) nch_items = (nrows + kTileRows - 1) / kTileRows;
+        if (nch_hi < nch_items) nch_hi = nch_items;
+        if (nch_lo < 1) nch_lo = 1;
+        if (nch_hi < nch_lo) nch_hi = nch_lo;
+        int best_rb = kTileRows;
+        double best = 1e30;
+        for (int64_t nch = nch_lo; nch <= nch_hi; ++nch) {
+            const int64_t rb = ((nrows + nch - 1) / nch + kTileRows - 1) / kTileRows * kTileRows;
+            const int64_t chunks = (nrows + rb - 1) / rb;
+            const double items = (double)nstrips * (double)chunks;
+            const double cost = ceil(items / kCtaSlots) * ((double)rb + 96.0);  // rows per CTA slot + per-CTA overhead
+            if (cost < best * 0.999) {
+                best = cost;
+                best_rb = (int)rb;
+            }
+        }
+        return best_rb;
     }
     // largest chunk that still gives >= ~6 CTAs per SM (148 SMs); bounds the partial buffers
     const int64_t want = 148 * 6;
@@ -588,7 +628,7 @@ int pick_rows_per_cta(int64_t nrows, int nstrips, int variant) {
 
 struct Layout {
     int nstrips, rb, nchunks;
-    size_t off_counts, off_gpart, off_mpart, total;
+    size_t off_counts, off_gpart, off_mpart, off_spart, total;
 };
 
 Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant) {
@@ -599,7 +639,8 @@ Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant) {
     L.nchunks = (int)((nrows + L.rb - 1) / L.rb);
     if (L.nchunks < 1) L.nchunks = 1;
     L.off_counts = 0;
-    L.off_mpart = align_up(sizeof(unsigned) * (size_t)(L.nstrips + 1), 256);
+    L.off_spart = align_up(sizeof(unsigned) * (size_t)(L.nstrips + 1), 256);
+    L.off_mpart = L.off_spart + align_up(sizeof(double) * kNM * (size_t)L.nstrips, 256);
     L.off_gpart = L.off_mpart + align_up(sizeof(double) * kNM * (size_t)L.nstrips * L.nchunks, 256);
     L.total = L.off_gpart + sizeof(float) * (size_t)kCols * 3 * L.nstrips * L.nchunks;
     return L;
@@ -715,6 +756,7 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     P.strip_count = reinterpret_cast<unsigned*>(ws + L.off_counts);
     P.done_count = P.strip_count + L.nstrips;
     P.mpart = reinterpret_cast<double*>(ws + L.off_mpart);
+    P.spart = reinterpret_cast<double*>(ws + L.off_spart);
     P.gpart = reinterpret_cast<float*>(ws + L.off_gpart);
     dim3 grid(L.nstrips, L.nchunks);
     cudaError_t err = cudaSuccess;
