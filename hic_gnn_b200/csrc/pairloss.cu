@@ -160,7 +160,8 @@ struct Params {
     const float* coords;
     const float* target;  // points at row r0
     int64_t pitch;
-    int n, r0, r1, rb, nstrips, nchunks;
+    int n, r0, r1, rb, nstrips, nchunks;  // nchunks = grid.y = chunk slots per strip (staggered strips use one more than the others)
+    int stagger;                          // 1: strips with odd (strip / 148) start half a chunk early (see chunk_rows)
     float c_mse, c_l1;
     double* moments;
     float* grad;
@@ -247,6 +248,22 @@ __device__ __forceinline__ void process_group(Acc& a, const ColumnRegs& c, const
     }
 }
 
+// Row range of (strip, chunk).  The two CTAs that share an SM start together and, with equal
+// chunks, would also finish together: both slots then sit in their epilogue / prologue at the same
+// time and the SM's share of HBM idles once per wave.  The first wave puts CTAs 148..295 (strips
+// 148..295 of chunk 0) into the second slot of every SM, so those strips get their chunk boundaries
+// shifted by half a chunk: their first item is half as long and the two slots stay half a period
+// apart for the rest of the kernel.  Returns the number of chunks of this strip.
+__device__ __forceinline__ int chunk_rows(const Params& P, int strip, int chunk, int& row_begin, int& nrows) {
+    const int total = P.r1 - P.r0;
+    const int off = (P.stagger && ((strip / 148) & 1)) ? (P.rb >> 1) : 0;
+    const int count = (total + off + P.rb - 1) / P.rb;
+    const int start = max(0, chunk * P.rb - off), end = min(total, (chunk + 1) * P.rb - off);
+    row_begin = P.r0 + start;
+    nrows = max(0, end - start);
+    return count;
+}
+
 struct CombineSmem {
     float g[kWarps][kCols * 3 + 4];
     double m[kWarps][kNM];
@@ -298,7 +315,7 @@ __device__ __forceinline__ void park_warp(const Acc& a, CombineSmem& S, int warp
 // CTA-level combine + cross-CTA fixed-order reduction.  Called by ALL threads of the block after
 // a __syncthreads() that follows park_warp(); nthreads = blockDim.x.
 template <uint32_t MODE>
-__device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int strip, int chunk, int tid, int nthreads) {
+__device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int strip, int chunk, int count, int tid, int nthreads) {
     const int n = P.n;
     const int cta = chunk * P.nstrips + strip;
     if constexpr ((MODE & 3u) != 0) {
@@ -326,7 +343,7 @@ __device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int 
         __threadfence();  // acquire side for the last CTA of the strip
     }
     __syncthreads();
-    if (S.ticket[0] != (unsigned)(P.nchunks - 1)) return;
+    if (S.ticket[0] != (unsigned)(count - 1)) return;
     // ---- last CTA of this column strip: add the strip's row-chunk partials in chunk order
     if constexpr ((MODE & 3u) != 0) {
         const float scale = ((MODE & 3u) == HICGAT_PAIR_GRAD_MSE) ? P.c_mse
@@ -336,12 +353,12 @@ __device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int 
             const size_t stride = (size_t)P.nstrips * (kCols * 3);
             double s = 0.0;
             int c = 0;
-            for (; c + 4 <= P.nchunks; c += 4) {  // 4 independent loads in flight, summed in chunk order
+            for (; c + 4 <= count; c += 4) {  // 4 independent loads in flight, summed in chunk order
                 const float v0 = __ldcg(src + (size_t)c * stride), v1 = __ldcg(src + (size_t)(c + 1) * stride);
                 const float v2 = __ldcg(src + (size_t)(c + 2) * stride), v3 = __ldcg(src + (size_t)(c + 3) * stride);
                 s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
             }
-            for (; c < P.nchunks; ++c) s += (double)__ldcg(src + (size_t)c * stride);
+            for (; c < count; ++c) s += (double)__ldcg(src + (size_t)c * stride);
             const int col = strip * kCols + i / 3;
             if (col < n) {
                 const double v = s * (double)scale;
@@ -350,9 +367,17 @@ __device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int 
             }
         }
     }
-    if (tid < kNM) {  // the strip's moments -> one partial per strip
+    if (tid < kNM) {  // the strip's moments -> one partial per strip (loads batched, added in chunk order)
+        const double* src = P.mpart + (size_t)strip * kNM + tid;
+        const size_t stride = (size_t)P.nstrips * kNM;
         double s = 0.0;
-        for (int c = 0; c < P.nchunks; ++c) s += __ldcg(P.mpart + ((size_t)c * P.nstrips + strip) * kNM + tid);
+        int c = 0;
+        for (; c + 4 <= count; c += 4) {
+            const double v0 = __ldcg(src + (size_t)c * stride), v1 = __ldcg(src + (size_t)(c + 1) * stride);
+            const double v2 = __ldcg(src + (size_t)(c + 2) * stride), v3 = __ldcg(src + (size_t)(c + 3) * stride);
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; c < count; ++c) s += __ldcg(src + (size_t)c * stride);
         __stcg(P.spart + (size_t)strip * kNM + tid, s);
     }
     __syncthreads();
@@ -363,10 +388,29 @@ __device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int 
     }
     __syncthreads();
     if (S.ticket[1] != (unsigned)(P.nstrips - 1)) return;
-    // ---- last strip to finish: fixed-order f64 reduction of the per-strip moment partials
+    // ---- last strip to finish: f64 reduction of the per-strip moment partials in a FIXED order
+    // (thread t takes strips t, t+256, ...; then lanes, then warps): the whole CTA works on it,
+    // because this is the serial tail of the kernel
+    double m[kNM];
+#pragma unroll
+    for (int k = 0; k < kNM; ++k) m[k] = 0.0;
+    if (tid < kThreads) {
+        for (int st = tid; st < P.nstrips; st += kThreads) {
+#pragma unroll
+            for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.spart + (size_t)st * kNM + k);
+        }
+#pragma unroll
+        for (int k = 0; k < kNM; ++k) m[k] = warp_sum(m[k]);
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < kNM; ++k) S.m[tid >> 5][k] = m[k];
+        }
+    }
+    __syncthreads();
     if (tid < kNM) {
         double s = 0.0;
-        for (int st = 0; st < P.nstrips; ++st) s += __ldcg(P.spart + (size_t)st * kNM + tid);
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += S.m[w][tid];
         P.moments[tid] = s;
     }
 }
@@ -383,9 +427,9 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_ldg_kernel(const Params 
     const int strip = blockIdx.x, chunk = blockIdx.y;
     const int n = P.n;
     const int col0 = strip * kCols + lane * 4;
-    const int row_begin = P.r0 + chunk * P.rb;
-    const int row_end = min(row_begin + P.rb, P.r1);
-    const int nrows = row_end - row_begin;
+    int row_begin, nrows;
+    const int count = chunk_rows(P, strip, chunk, row_begin, nrows);
+    if (chunk >= count) return;  // unstaggered strips leave the extra chunk slot empty
     const bool edge = (strip + 1) * kCols > n;
 
     for (int r = threadIdx.x; r < nrows; r += kThreads) {
@@ -422,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_ldg_kernel(const Params 
     }
     park_warp<MODE>(a, S, warp, lane);
     __syncthreads();
-    finish_cta<MODE>(P, S, strip, chunk, threadIdx.x, kThreads);
+    finish_cta<MODE>(P, S, strip, chunk, count, threadIdx.x, kThreads);
 }
 
 // ------------------------------------------------------------------ variant 0: TMA + mbarrier ring
@@ -484,9 +528,9 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_tma_kernel(const __grid_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strip = blockIdx.x, chunk = blockIdx.y;
     const int n = P.n;
-    const int row_begin = P.r0 + chunk * P.rb;
-    const int row_end = min(row_begin + P.rb, P.r1);
-    const int nrows = row_end - row_begin;
+    int row_begin, nrows;
+    const int count = chunk_rows(P, strip, chunk, row_begin, nrows);
+    if (chunk >= count) return;  // unstaggered strips leave the extra chunk slot empty
     const int ntiles = (nrows + kTileRows - 1) / kTileRows;
     const int col0 = strip * kCols + lane * 4;
     const bool edge = (strip + 1) * kCols > n;
@@ -552,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_tma_kernel(const __grid_
     CombineSmem& S = *reinterpret_cast<CombineSmem*>(ring);
     park_warp<MODE>(a, S, warp, lane);
     __syncthreads();
-    finish_cta<MODE>(P, S, strip, chunk, threadIdx.x, kThreads);
+    finish_cta<MODE>(P, S, strip, chunk, count, threadIdx.x, kThreads);
 }
 
 // ------------------------------------------------------------------ materialising variant
@@ -588,6 +632,7 @@ __global__ void pairdist_bwd_kernel(const float* __restrict__ coords, int n, con
 
 // ------------------------------------------------------------------ host side
 int g_rows_per_cta = 0;
+int g_stagger = 1;
 int g_variant = 0;  // 0 = TMA ring (default), 1 = per-lane streaming loads
 
 int pick_rows_per_cta(int64_t nrows, int nstrips, int variant) {
@@ -627,7 +672,7 @@ int pick_rows_per_cta(int64_t nrows, int nstrips, int variant) {
 }
 
 struct Layout {
-    int nstrips, rb, nchunks;
+    int nstrips, rb, nchunks, stagger;
     size_t off_counts, off_gpart, off_mpart, off_spart, total;
 };
 
@@ -638,6 +683,9 @@ Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant) {
     L.rb = pick_rows_per_cta(nrows, L.nstrips, variant);
     L.nchunks = (int)((nrows + L.rb - 1) / L.rb);
     if (L.nchunks < 1) L.nchunks = 1;
+    // stagger (chunk_rows): only where a second CTA slot per SM is filled in the first wave
+    L.stagger = (variant == 0 && g_stagger && L.nstrips > 148 && L.nchunks >= 2) ? 1 : 0;
+    if (L.stagger) L.nchunks = (int)((nrows + L.rb / 2 + L.rb - 1) / L.rb);
     L.off_counts = 0;
     L.off_spart = align_up(sizeof(unsigned) * (size_t)(L.nstrips + 1), 256);
     L.off_mpart = L.off_spart + align_up(sizeof(double) * kNM * (size_t)L.nstrips, 256);
@@ -701,12 +749,13 @@ extern "C" int hicgat_pairloss_set_tuning(int rows_per_cta, int variant) {
         set_error("hicgat_pairloss_set_tuning: rows_per_cta must be 0 or a multiple of 8 in [8,4096]");
         return HICGAT_ERR_INVALID;
     }
-    if (variant != 0 && variant != 1) {
-        set_error("hicgat_pairloss_set_tuning: variant must be 0 (TMA ring) or 1 (per-lane loads)");
+    if (variant < 0 || variant > 2) {
+        set_error("hicgat_pairloss_set_tuning: variant must be 0 (TMA ring), 1 (per-lane loads) or 2 (TMA ring, unstaggered chunks)");
         return HICGAT_ERR_INVALID;
     }
     g_rows_per_cta = rows_per_cta;
-    g_variant = variant;
+    g_variant = variant == 2 ? 0 : variant;
+    g_stagger = variant == 2 ? 0 : 1;
     return HICGAT_OK;
 }
 
@@ -751,7 +800,7 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     }
     Params P;
     P.coords = coords; P.target = target; P.pitch = pitch;
-    P.n = (int)n; P.r0 = (int)r0; P.r1 = (int)r1; P.rb = L.rb; P.nstrips = L.nstrips; P.nchunks = L.nchunks;
+    P.n = (int)n; P.r0 = (int)r0; P.r1 = (int)r1; P.rb = L.rb; P.nstrips = L.nstrips; P.nchunks = L.nchunks; P.stagger = L.stagger;
     P.c_mse = c_mse; P.c_l1 = c_l1; P.moments = moments; P.grad = grad; P.grad64 = grad64;
     P.strip_count = reinterpret_cast<unsigned*>(ws + L.off_counts);
     P.done_count = P.strip_count + L.nstrips;

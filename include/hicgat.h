@@ -94,7 +94,8 @@ HICGAT_API int hicgat_pairloss_fwd_bwd_packed(const float* coords, const float* 
                                    float c_l1, double* packed, void* workspace,
                                    size_t workspace_bytes, hicgat_stream_t stream);
 /* Tuning hook (bench/tests): rows per CTA row-chunk (0 = library default) and kernel variant:
- * 0 = TMA tile ring (cp.async.bulk.tensor + mbarrier, default), 1 = per-lane streaming loads. */
+ * 0 = TMA tile ring (cp.async.bulk.tensor + mbarrier, default), 1 = per-lane streaming loads,
+ * 2 = TMA tile ring without the half-chunk stagger of the second CTA slot (A/B only). */
 HICGAT_API int hicgat_pairloss_set_tuning(int rows_per_cta, int variant);
 
 /* ------------------------------------------------------------------------------------
