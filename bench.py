@@ -352,20 +352,22 @@ def run_native(args):
         torch.cuda.empty_cache()
 
     # ---- (1) resident loss step: fused kernel on the local rows + one packed all-reduce + unpack
-    raw_local_fn = sharding.cuda_local_fn(target, mode, c_mse, c_l1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cursor = {"k": None}
 
-    def local_fn(c, packed):  # the fused kernel, bracketed by events inside the timed region
-        k = cursor["k"]
-        if k is not None:
-            ev[k][0].record()
-        raw_local_fn(c, packed)
-        if k is not None:
-            ev[k][1].record()
+    def timed(raw):  # the fused kernel, bracketed by events inside the timed region
+        def fn(*a):
+            k = cursor["k"]
+            if k is not None:
+                ev[k][0].record()
+            raw(*a)
+            if k is not None:
+                ev[k][1].record()
+        return fn
 
-    loss_fn = sharding.make_sharded_pair_loss(n, local_fn, dev, transport=args.transport)
+    loss_fn = sharding.make_sharded_pair_loss(n, timed(sharding.cuda_local_fn(target, mode, c_mse, c_l1)), dev, transport=args.transport,
+                                              local_split_fn=timed(sharding.cuda_local_split_fn(target, mode, c_mse, c_l1)))
     transport = "none" if world == 1 else ("p2p_oneshot" if isinstance(loss_fn, sharding.P2PShardedPairLoss) else "nccl_allreduce")
 
     def loss_step(k=None):

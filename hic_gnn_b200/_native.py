@@ -25,7 +25,7 @@ SIGNATURES = {
     "hicgat_pairloss_fwd_bwd": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _p, _sz, _p]),
     "hicgat_pairloss_fwd_bwd_packed": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _sz, _p]),
     "hicgat_pairloss_set_tuning": (C.c_int, [_i32, _i32]),
-    "hicgat_allreduce_packed_p2p": (C.c_int, [_p, _p, _i32, _i32, _i64, _i64, _i32, _u32, _p, _p, _p, _p]),
+    "hicgat_allreduce_partials_p2p": (C.c_int, [_p, _p, _i32, _i32, _i64, _i64, _i32, _u32, _p, _p, _p, _p]),
     "hicgat_pairdist_fwd": (C.c_int, [_p, _i64, _p, _i64, _p]),
     "hicgat_pairdist_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _p]),
     "hicgat_cont2dist_max_f64": (C.c_int, [_p, _i64, _i64, _i64, _i64, _f64, _p, _p, _sz, _p]),
@@ -44,7 +44,7 @@ SIGNATURES = {
     "hicgat_gat_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
-PAIR_GRAD_MSE, PAIR_GRAD_L1, PAIR_MOMENTS, PAIR_MOMENTS_D, PAIR_NMOM = 1, 2, 4, 8, 8
+PAIR_GRAD_MSE, PAIR_GRAD_L1, PAIR_MOMENTS, PAIR_MOMENTS_D, PAIR_WS_CLEAN, PAIR_NMOM = 1, 2, 4, 8, 16, 8
 
 _lib = None
 

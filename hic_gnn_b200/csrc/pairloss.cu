@@ -344,6 +344,7 @@ __device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int 
     }
     __syncthreads();
     if (S.ticket[0] != (unsigned)(count - 1)) return;
+    if (tid == 0) P.strip_count[strip] = 0u;  // leave the counters zeroed for the next call (HICGAT_PAIR_WS_CLEAN)
     // ---- last CTA of this column strip: add the strip's row-chunk partials in chunk order
     if constexpr ((MODE & 3u) != 0) {
         const float scale = ((MODE & 3u) == HICGAT_PAIR_GRAD_MSE) ? P.c_mse
@@ -388,6 +389,7 @@ __device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int 
     }
     __syncthreads();
     if (S.ticket[1] != (unsigned)(P.nstrips - 1)) return;
+    if (tid == 0) *P.done_count = 0u;
     // ---- last strip to finish: f64 reduction of the per-strip moment partials in a FIXED order
     // (thread t takes strips t, t+256, ...; then lanes, then warps): the whole CTA works on it,
     // because this is the serial tail of the kernel
@@ -776,7 +778,9 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     HICGAT_REQUIRE(coords && (target || r0 == r1) && moments && workspace, "hicgat_pairloss_fwd_bwd: null pointer");
     HICGAT_REQUIRE(pitch >= n && (pitch % 4) == 0, "hicgat_pairloss_fwd_bwd: pitch %lld must be >= n and a multiple of 4", (long long)pitch);
     HICGAT_REQUIRE(aligned16(target), "hicgat_pairloss_fwd_bwd: target must be 16-byte aligned");  // NULL passes
-    HICGAT_REQUIRE((mode & ~15u) == 0, "hicgat_pairloss_fwd_bwd: unknown mode bits 0x%x", mode);
+    HICGAT_REQUIRE((mode & ~31u) == 0, "hicgat_pairloss_fwd_bwd: unknown mode bits 0x%x", mode);
+    const bool ws_clean = (mode & HICGAT_PAIR_WS_CLEAN) != 0;
+    mode &= ~HICGAT_PAIR_WS_CLEAN;
     if (mode & HICGAT_PAIR_MOMENTS) mode &= ~HICGAT_PAIR_MOMENTS_D;          // full moments include the light set
     if ((mode & HICGAT_PAIR_MOMENTS_D) && (mode & HICGAT_PAIR_GRAD_L1)) {     // the L1 value needs sum |d-t|: full set
         mode = (mode & ~HICGAT_PAIR_MOMENTS_D) | HICGAT_PAIR_MOMENTS;
@@ -791,7 +795,7 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
         return HICGAT_ERR_WORKSPACE;
     }
     unsigned char* ws = static_cast<unsigned char*>(workspace);
-    HICGAT_CUDA(cudaMemsetAsync(ws + L.off_counts, 0, sizeof(unsigned) * (size_t)(L.nstrips + 1), stream));
+    if (!ws_clean) HICGAT_CUDA(cudaMemsetAsync(ws + L.off_counts, 0, sizeof(unsigned) * (size_t)(L.nstrips + 1), stream));
     if (r1 == r0) {  // empty row block: contributes nothing
         HICGAT_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * kNM, stream));
         if (grad) HICGAT_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * 3 * (size_t)n, stream));

@@ -101,7 +101,8 @@ class _PairWorkspace:
         ws = cls._cache.get(key)
         if ws is None:
             need = N.lib().hicgat_pairloss_workspace_bytes(n, r0, r1)
-            ws = torch.empty(need, dtype=torch.uint8, device=device)
+            # zero-filled once and used for nothing else: calls pass HICGAT_PAIR_WS_CLEAN
+            ws = torch.zeros(need, dtype=torch.uint8, device=device)
             cls._cache[key] = ws
         return ws
 
@@ -119,7 +120,7 @@ def pairloss_raw(coords: torch.Tensor, target: WishTarget, mode: int, c_mse: flo
         grad = torch.empty(n, 3, dtype=torch.float32, device=coords.device)
     ws = _PairWorkspace.get(coords.device, n, target.r0, target.r1)
     rc = N.lib().hicgat_pairloss_fwd_bwd(
-        coords.data_ptr(), target.data.data_ptr(), target.pitch, n, target.r0, target.r1, mode, c_mse, c_l1,
+        coords.data_ptr(), target.data.data_ptr(), target.pitch, n, target.r0, target.r1, mode | N.PAIR_WS_CLEAN, c_mse, c_l1,
         moments.data_ptr(), _ptr(grad), ws.data_ptr(), ws.numel(), _stream(),
     )
     N.check(rc, "hicgat_pairloss_fwd_bwd")
@@ -183,11 +184,13 @@ def sharded_reducer(target: WishTarget, mode: str, group=None, transport: str = 
     n = target.n
     npairs = n * (n - 1) / 2.0
     m = _MODES[mode]
-    fn = sharding.cuda_local_fn(target, m, 4.0 / (float(n) * float(n)), 0.1 / max(npairs, 1.0))
+    c_mse, c_l1 = 4.0 / (float(n) * float(n)), 0.1 / max(npairs, 1.0)
+    fn = sharding.cuda_local_fn(target, m, c_mse, c_l1)
+    split_fn = sharding.cuda_local_split_fn(target, m, c_mse, c_l1)
     const = None
     if m & N.PAIR_MOMENTS_D and not m & N.PAIR_MOMENTS:
         const = sharding.allreduce_packed(target.t_moments().clone(), group)  # global sum t, sum t^2: once
-    return sharding.make_sharded_pair_loss(n, fn, target.data.device, group, moment_const=const, transport=transport)
+    return sharding.make_sharded_pair_loss(n, fn, target.data.device, group, moment_const=const, transport=transport, local_split_fn=split_fn)
 
 
 def pair_moments(coords: torch.Tensor, target: WishTarget) -> torch.Tensor:
@@ -326,7 +329,7 @@ class HostPairLoss:
             ws = _PairWorkspace.get(self.device, self.n, self.r0 + lo, self.r0 + hi)
             rc = lib.hicgat_pairloss_fwd_bwd_packed(
                 self.coords_dev.data_ptr(), self.stage[s].data_ptr(), self.pitch, self.n, self.r0 + lo, self.r0 + hi,
-                mode, c_mse, c_l1, self.packed.data_ptr(), ws.data_ptr(), ws.numel(), main.cuda_stream,
+                mode | N.PAIR_WS_CLEAN, c_mse, c_l1, self.packed.data_ptr(), ws.data_ptr(), ws.numel(), main.cuda_stream,
             )
             N.check(rc, "hicgat_pairloss_fwd_bwd_packed")
             self.acc.add_(self.packed)

@@ -66,10 +66,11 @@ class ShardedPairLoss:
 
 class P2PShardedPairLoss:
     """Same contract as :class:`ShardedPairLoss`, but the exchange is the hand-written one-shot
-    all-reduce over NVLink peer memory (``hicgat_allreduce_packed_p2p``): the fused loss kernel
-    writes its packed partial into a symmetric buffer that every rank maps, then ONE kernel per
-    rank does barrier + rank-ordered sum + unpack.  Two buffer halves alternate by step parity
-    (see csrc/comm.cu for why that makes a trailing barrier unnecessary)."""
+    all-reduce over NVLink peer memory (``hicgat_allreduce_partials_p2p``): the fused loss kernel
+    writes its partial ``[8 x f64 moments | 3n x f32 gradient]`` straight into a symmetric buffer
+    that every rank maps, then ONE kernel per rank does barrier + rank-ordered sum.  Two buffer
+    halves alternate by step parity (see csrc/comm.cu for why that makes a trailing barrier
+    unnecessary).  ``local_fn(coords, moments_f64[8], grad_f32[n,3])`` fills the local partial."""
 
     SLOT_BASE = 256  # uint32 slot offset inside torch's signal pad (its own barriers use the low channels)
 
@@ -80,9 +81,8 @@ class P2PShardedPairLoss:
 
         group = group if group is not None else dist.group.WORLD
         self.n, self.local_fn = n, local_fn
-        self.count = N.PAIR_NMOM + 3 * n
-        self.half = (self.count + 1) // 2 * 2  # keeps the second half 16-byte aligned
-        self.buf = symm.empty(2 * self.half, dtype=torch.float64, device=device)
+        self.half_bytes = (64 + 12 * n + 15) // 16 * 16
+        self.buf = symm.empty(2 * self.half_bytes, dtype=torch.uint8, device=device)
         self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, group)
         self.world, self.rank = self.hdl.world_size, self.hdl.rank
@@ -91,6 +91,9 @@ class P2PShardedPairLoss:
         self._bufs = (C.c_uint64 * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
         self._pads = (C.c_uint64 * self.world)(*[int(p) for p in self.hdl.signal_pad_ptrs])
         self.moment_const = moment_const
+        # typed views of the two halves of the local partial
+        self.part_m = [self.buf[h * self.half_bytes: h * self.half_bytes + 64].view(torch.float64) for h in range(2)]
+        self.part_g = [self.buf[h * self.half_bytes + 64: h * self.half_bytes + 64 + 12 * n].view(torch.float32).view(n, 3) for h in range(2)]
         self.out_m = [torch.empty(N.PAIR_NMOM, dtype=torch.float64, device=device) for _ in range(2)]
         self.out_g = [torch.empty(n, 3, dtype=torch.float32, device=device) for _ in range(2)]
         self.epoch = 0
@@ -100,32 +103,33 @@ class P2PShardedPairLoss:
     def __call__(self, coords: torch.Tensor):
         self.epoch += 1
         par = self.epoch & 1
-        packed = self.buf[par * self.half: par * self.half + self.count]
-        self.local_fn(coords, packed)
+        self.local_fn(coords, self.part_m[par], self.part_g[par])
         m, g = self.out_m[par], self.out_g[par]
-        rc = N.lib().hicgat_allreduce_packed_p2p(
-            self._bufs, self._pads, self.rank, self.world, self.n, par * self.half * 8, self.SLOT_BASE, self.epoch & 0xFFFFFFFF,
+        rc = N.lib().hicgat_allreduce_partials_p2p(
+            self._bufs, self._pads, self.rank, self.world, self.n, par * self.half_bytes, self.SLOT_BASE, self.epoch & 0xFFFFFFFF,
             None if self.moment_const is None else self.moment_const.data_ptr(), m.data_ptr(), g.data_ptr(),
             torch.cuda.current_stream().cuda_stream,
         )
-        N.check(rc, "hicgat_allreduce_packed_p2p")
+        N.check(rc, "hicgat_allreduce_partials_p2p")
         return m, g
 
 
-def make_sharded_pair_loss(n: int, local_fn, device, group=None, moment_const=None, transport: str = "auto"):
-    """``transport``: ``"p2p"`` (one-shot kernel over NVLink peer memory), ``"nccl"`` (packed
-    ``all_reduce``) or ``"auto"`` (p2p on CUDA with an initialised multi-rank NCCL group when the
-    symmetric-memory rendezvous succeeds, else nccl)."""
+def make_sharded_pair_loss(n: int, local_fn, device, group=None, moment_const=None, transport: str = "auto", local_split_fn=None):
+    """``transport``: ``"p2p"`` (one-shot kernel over NVLink peer memory; needs ``local_split_fn``),
+    ``"nccl"`` (packed ``all_reduce``; uses ``local_fn``) or ``"auto"`` (p2p on CUDA with an
+    initialised multi-rank NCCL group when the symmetric-memory rendezvous succeeds, else nccl)."""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    if transport == "p2p" or (transport == "auto" and multi and torch.device(device).type == "cuda"):
+    if local_split_fn is not None and (transport == "p2p" or (transport == "auto" and multi and torch.device(device).type == "cuda")):
         try:
-            return P2PShardedPairLoss(n, local_fn, device, group, moment_const)
+            return P2PShardedPairLoss(n, local_split_fn, device, group, moment_const)
         except Exception as e:  # no symmetric memory on this system: the NCCL exchange is equivalent
             if transport == "p2p":
                 raise
             import warnings
 
             warnings.warn(f"symmetric-memory exchange unavailable ({e!r}); using the NCCL all-reduce")
+    elif transport == "p2p":
+        raise RuntimeError("transport='p2p' needs local_split_fn")
     return ShardedPairLoss(n, local_fn, device, group, moment_const)
 
 
@@ -138,8 +142,25 @@ def cuda_local_fn(target, mode: int, c_mse: float, c_l1: float):
         ws = _PairWorkspace.get(coords.device, target.n, target.r0, target.r1)
         rc = N.lib().hicgat_pairloss_fwd_bwd_packed(
             coords.contiguous().data_ptr(), target.data.data_ptr(), target.pitch, target.n, target.r0, target.r1,
-            mode, c_mse, c_l1, packed.data_ptr(), ws.data_ptr(), ws.numel(), _stream(),
+            mode | N.PAIR_WS_CLEAN, c_mse, c_l1, packed.data_ptr(), ws.data_ptr(), ws.numel(), _stream(),
         )
         N.check(rc, "hicgat_pairloss_fwd_bwd_packed")
+
+    return fn
+
+
+def cuda_local_split_fn(target, mode: int, c_mse: float, c_l1: float):
+    """``local_fn`` of :class:`P2PShardedPairLoss`: hicgat_pairloss_fwd_bwd writing moments / grad
+    straight into the symmetric partial."""
+    from .ops import _PairWorkspace, _cuda, _stream
+
+    def fn(coords: torch.Tensor, moments: torch.Tensor, grad: torch.Tensor):
+        _cuda(coords, moments, grad)
+        ws = _PairWorkspace.get(coords.device, target.n, target.r0, target.r1)
+        rc = N.lib().hicgat_pairloss_fwd_bwd(
+            coords.contiguous().data_ptr(), target.data.data_ptr(), target.pitch, target.n, target.r0, target.r1,
+            mode | N.PAIR_WS_CLEAN, c_mse, c_l1, moments.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(), _stream(),
+        )
+        N.check(rc, "hicgat_pairloss_fwd_bwd")
 
     return fn

@@ -79,6 +79,10 @@ HICGAT_API uint64_t hicgat_launch_count(void);
  * as 0).  sum t and sum t^2 are constants of the target: take them ONCE from a
  * HICGAT_PAIR_MOMENTS launch.  Implied by HICGAT_PAIR_MOMENTS. */
 #define HICGAT_PAIR_MOMENTS_D 8u
+/* The ticket counters at the start of `workspace` (4*(ceil(n/128)+1) bytes) are known to be zero:
+ * skips the reset memset.  Every successful call leaves them zeroed, so a caller that zero-fills
+ * a workspace once and uses it for nothing else may set this bit on every call. */
+#define HICGAT_PAIR_WS_CLEAN 16u
 #define HICGAT_PAIR_NMOM 8
 
 HICGAT_API size_t hicgat_pairloss_workspace_bytes(int64_t n, int64_t r0, int64_t r1);
@@ -99,21 +103,22 @@ HICGAT_API int hicgat_pairloss_fwd_bwd_packed(const float* coords, const float* 
 HICGAT_API int hicgat_pairloss_set_tuning(int rows_per_cta, int variant);
 
 /* ------------------------------------------------------------------------------------
- * (3) Exchange step of the row-sharded loss: one-shot all-reduce of every rank's
- * packed f64[8 + 3n] partial over NVLink peer memory (no counterpart in the reference, which is
- * single-process).  Each rank's packed buffer lives in a SYMMETRIC
- * allocation mapped by all ranks; `peer_bufs_host[r]` / `signal_pads_host[r]` are HOST arrays of
- * the device addresses of rank r's buffer and signal pad in THIS process's address space.
- * The kernel signals epoch `epoch` to all peers (uint32 slots `slot_base + rank` of their pads),
- * waits for all peers, sums the partials at `buf_offset_bytes` in rank order (bit-identical on
- * every rank) and writes moments f64[8] (+ `moment_const` if not NULL) and grad f32[n,3].
- * Callers alternate two buffer halves by epoch parity and increase `epoch` by one per call,
- * starting at 1 (pads zero-initialised); no other synchronisation is needed.
+ * (3) Exchange step of the row-sharded loss: one-shot all-reduce of every rank's partial
+ * [8 x f64 moments | 3n x f32 gradient] (64 + 12n bytes, what hicgat_pairloss_fwd_bwd writes when
+ * given moments = base and grad = base + 64 bytes) over NVLink peer memory.  No counterpart in
+ * the reference, which is single-process.  Each rank's partial lives in a
+ * SYMMETRIC allocation mapped by all ranks; `peer_bufs_host[r]` / `signal_pads_host[r]` are HOST
+ * arrays of the device addresses of rank r's buffer and signal pad in THIS process's address
+ * space.  The kernel signals epoch `epoch` to all peers (uint32 slots `slot_base + rank` of
+ * their pads), waits for all peers, sums the partials at `buf_offset_bytes` in rank order
+ * (bit-identical on every rank) and writes moments f64[8] (+ `moment_const` if not NULL) and
+ * grad f32[n,3].  Callers alternate two buffer halves by epoch parity and increase `epoch` by
+ * one per call, starting at 1 (pads zero-initialised); no other synchronisation is needed.
  * ---------------------------------------------------------------------------------- */
-HICGAT_API int hicgat_allreduce_packed_p2p(const uint64_t* peer_bufs_host, const uint64_t* signal_pads_host, int rank,
-                                int world, int64_t n, int64_t buf_offset_bytes, int slot_base, uint32_t epoch,
-                                const double* moment_const, double* out_moments, float* out_grad,
-                                hicgat_stream_t stream);
+HICGAT_API int hicgat_allreduce_partials_p2p(const uint64_t* peer_bufs_host, const uint64_t* signal_pads_host, int rank,
+                                  int world, int64_t n, int64_t buf_offset_bytes, int slot_base, uint32_t epoch,
+                                  const double* moment_const, double* out_moments, float* out_grad,
+                                  hicgat_stream_t stream);
 
 /* Materialising variant kept for API parity of model.forward() (returns the N x N matrix,
  * models.py:39): dist[i,j] = |x_i - x_j|, and its backward
