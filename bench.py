@@ -472,6 +472,13 @@ def run_native(args):
         except Exception:
             peak = 6650.0
         achieved = nloc * n * 4.0 / (kern_ms * 1e-3) / 1e9
+        traffic = None  # DRAM bytes per launch from the committed ncu capture of this exact shape, if there is one
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "r1_pairloss_traffic.json"))).get(f"{nloc}x{n}")
+            if t and args.variant == 0:
+                traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"])
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -479,7 +486,7 @@ def run_native(args):
                        "parallelism": f"rows{world}" if world > 1 else ("single" if not args.emulate_world else f"rank0-of-{args.emulate_world} (emulated, NOT a bench line)"), "rows_per_rank": nloc, "exchange": transport,
                        "l2": f"no flush: each step streams {target_bytes / 1e6:.0f} MB of target per rank (L2 is 126 MB)",
                        "setup_s": round(t_setup, 1)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "pairloss_tma_kernel" if args.variant == 0 else "pairloss_ldg_kernel", "kernel_ms": kern_ms, "algorithmic_bytes": nloc * n * 4.0, "peak_source": peak_src,
                          "frac_of_spec_8000": achieved / 8000.0,
                          "copy_gbs_this_run": copy_gbs, "frac_of_copy_this_run": (achieved / copy_gbs) if copy_gbs else None},
