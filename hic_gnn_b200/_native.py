@@ -41,6 +41,14 @@ SIGNATURES = {
     "hicgat_csr_transpose_perm": (C.c_int, [_p, _p, _i64, _p, _p]),
     "hicgat_gat_fwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),
     "hicgat_gat_bwd_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "hicgat_gat_logits": (C.c_int, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "hicgat_gat_dense_mask_words": (_sz, [_i64]),
+    "hicgat_gat_dense_build_mask": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "hicgat_gat_dense_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "hicgat_gat_dense_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p, _sz, _p]),
+    "hicgat_gat_dense_bwd": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "hicgat_gat_param_grads_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "hicgat_gat_param_grads": (C.c_int, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hicgat_gat_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 

@@ -528,3 +528,45 @@ extern "C" int hicgat_gat_bwd(const int32_t* rowptr, const int32_t* col, const i
     HICGAT_CHECK_LAUNCH("gat_bwd_param_kernel");
     return HICGAT_OK;
 }
+
+// ------------------------------------------------------------------ pieces shared with the dense-tile path (gat_dense.cu)
+extern "C" int hicgat_gat_logits(int64_t n, int heads, int channels, const float* xl, const float* att_l, const float* att_r,
+                                 float* a_src, float* a_dst, hicgat_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HICGAT_REQUIRE(xl && att_l && att_r && a_src && a_dst && n > 0 && n < (1ll << 31), "hicgat_gat_logits: bad arguments");
+    HICGAT_REQUIRE(supported(heads, channels), "hicgat_gat_logits: unsupported heads=%d channels=%d", heads, channels);
+    HICGAT_REQUIRE(aligned16(xl) && aligned16(att_l) && aligned16(att_r), "hicgat_gat_logits: 16-byte alignment required");
+    const unsigned grid = (unsigned)((n + kRowsPerCta - 1) / kRowsPerCta);
+#define CALL_LOGIT(H, Q) gat_logit_kernel<H, Q><<<grid, 256, 0, stream>>>(xl, att_l, att_r, (int)n, a_src, a_dst)
+    HICGAT_DISPATCH_HQ(heads, channels, CALL_LOGIT);
+#undef CALL_LOGIT
+    HICGAT_CHECK_LAUNCH("gat_logit_kernel");
+    return HICGAT_OK;
+}
+
+extern "C" size_t hicgat_gat_param_grads_workspace_bytes(int64_t n, int heads, int channels) {
+    if (n <= 0 || !supported(heads, channels)) return 0;
+    return 256 + sizeof(float) * 3 * (size_t)heads * channels * (size_t)((n + kParamRows - 1) / kParamRows);
+}
+
+// datt_l[c] = sum_j d_a_src[j,h(c)] xl[j,c] ; datt_r[c] = sum_j d_a_dst[j,h(c)] xl[j,c] ; dbias[c] = sum_i g[i,c]
+extern "C" int hicgat_gat_param_grads(int64_t n, int heads, int channels, const float* xl, const float* gout, const float* d_a_src,
+                                      const float* d_a_dst, float* datt_l, float* datt_r, float* dbias, void* workspace,
+                                      size_t workspace_bytes, hicgat_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HICGAT_REQUIRE(xl && gout && d_a_src && d_a_dst && datt_l && datt_r && dbias && workspace && n > 0 && n < (1ll << 31), "hicgat_gat_param_grads: bad arguments");
+    HICGAT_REQUIRE(supported(heads, channels), "hicgat_gat_param_grads: unsupported heads=%d channels=%d", heads, channels);
+    const size_t need = hicgat_gat_param_grads_workspace_bytes(n, heads, channels);
+    if (workspace_bytes < need) {
+        set_error("hicgat_gat_param_grads: workspace %zu < required %zu", workspace_bytes, need);
+        return HICGAT_ERR_WORKSPACE;
+    }
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    unsigned* counter = reinterpret_cast<unsigned*>(ws);
+    float* part = reinterpret_cast<float*>(ws + 256);
+    HICGAT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
+    const int nchunks = (int)((n + kParamRows - 1) / kParamRows);
+    gat_bwd_param_kernel<<<nchunks, 256, 0, stream>>>(xl, gout, d_a_src, d_a_dst, (int)n, heads, channels, part, counter, datt_l, datt_r, dbias);
+    HICGAT_CHECK_LAUNCH("gat_bwd_param_kernel");
+    return HICGAT_OK;
+}

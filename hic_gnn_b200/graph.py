@@ -102,6 +102,22 @@ class CSRGraph:
 
         return self._get("self_loops", build)
 
+    def density(self) -> float:
+        """Fraction of all ordered pairs (incl. self loops) that are edges of the GAT pattern."""
+        return (self.nnz + self.n) / float(self.n * self.n)
+
+    def dense_mask(self):
+        """Bit mask u32[n, ceil(n/32)] of the self-loop pattern for the dense-tile GAT path."""
+
+        def build():
+            r32, c32, _ = self.with_self_loops()
+            words = (self.n + 31) // 32
+            mask = torch.empty(self.n, words, dtype=torch.int32, device=self.device)
+            N.check(N.lib().hicgat_gat_dense_build_mask(r32.data_ptr(), c32.data_ptr(), self.n, mask.data_ptr(), _stream()), "hicgat_gat_dense_build_mask")
+            return mask
+
+        return self._get("dense_mask", build)
+
     def sage_weights(self):
         """(norm_val, norm_val_t): D^-1 A values (layers.py:41-54) and their transposed-entry
         gather, both f32[nnz] in CSR order; built once."""

@@ -131,6 +131,56 @@ class _GatAttend(torch.autograd.Function):
         return dxl, datt_l.view(ctx.att_shape), datt_r.view(ctx.att_shape), dbias, None, None, None, None
 
 
+class _GatAttendDense(torch.autograd.Function):
+    """Dense-tile path of :class:`_GatAttend` for near-dense graphs (csrc/gat_dense.cu): the same
+    attention, evaluated as register-tiled fp32 GEMMs whose attention tiles are regenerated from
+    the logit halves, the row statistics and a bit mask of the pattern.  Saves O(N*H*C)."""
+
+    @staticmethod
+    def forward(ctx, xl, att_l, att_r, bias, graph: CSRGraph, heads: int, channels: int, slope: float):
+        _cuda(xl)
+        xl = xl.contiguous()
+        att_l_f, att_r_f, bias_f = att_l.contiguous().view(-1), att_r.contiguous().view(-1), bias.contiguous()
+        r32, c32, _ = graph.with_self_loops()
+        mask = graph.dense_mask()
+        n, dev, lib = graph.n, xl.device, N.lib()
+        a_src = torch.empty(n, heads, dtype=torch.float32, device=dev)
+        a_dst = torch.empty(n, heads, dtype=torch.float32, device=dev)
+        out = torch.empty(n, heads * channels, dtype=torch.float32, device=dev)
+        need = lib.hicgat_gat_dense_workspace_bytes(n, heads, channels)
+        if need == 0:
+            raise RuntimeError(f"dense GAT kernels do not support heads={heads}, channels={channels}")
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)  # holds the row statistics until backward
+        s = _stream()
+        N.check(lib.hicgat_gat_logits(n, heads, channels, xl.data_ptr(), att_l_f.data_ptr(), att_r_f.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(), s), "hicgat_gat_logits")
+        N.check(lib.hicgat_gat_dense_fwd(r32.data_ptr(), c32.data_ptr(), mask.data_ptr(), n, heads, channels, xl.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(),
+                                         bias_f.data_ptr(), slope, out.data_ptr(), ws.data_ptr(), ws.numel(), s), "hicgat_gat_dense_fwd")
+        ctx.save_for_backward(xl, att_l_f, att_r_f, bias_f, a_src, a_dst, out, ws)
+        ctx.graph, ctx.hc, ctx.slope, ctx.att_shape = graph, (heads, channels), slope, att_l.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xl, att_l_f, att_r_f, bias_f, a_src, a_dst, out, ws = ctx.saved_tensors
+        graph, (heads, channels) = ctx.graph, ctx.hc
+        g = g.contiguous()
+        n, dev, lib = graph.n, xl.device, N.lib()
+        mask = graph.dense_mask()
+        dxl = torch.empty_like(xl)
+        d_src = torch.empty(n, heads, dtype=torch.float32, device=dev)
+        d_dst = torch.empty(n, heads, dtype=torch.float32, device=dev)
+        datt_l, datt_r = torch.empty_like(att_l_f), torch.empty_like(att_r_f)
+        dbias = torch.empty(heads * channels, dtype=torch.float32, device=dev)
+        s = _stream()
+        N.check(lib.hicgat_gat_dense_bwd(mask.data_ptr(), n, heads, channels, xl.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(), att_l_f.data_ptr(), att_r_f.data_ptr(),
+                                         bias_f.data_ptr(), ctx.slope, out.data_ptr(), g.data_ptr(), dxl.data_ptr(), d_src.data_ptr(), d_dst.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), s), "hicgat_gat_dense_bwd")
+        pws = torch.empty(lib.hicgat_gat_param_grads_workspace_bytes(n, heads, channels), dtype=torch.uint8, device=dev)
+        N.check(lib.hicgat_gat_param_grads(n, heads, channels, xl.data_ptr(), g.data_ptr(), d_src.data_ptr(), d_dst.data_ptr(), datt_l.data_ptr(), datt_r.data_ptr(),
+                                           dbias.data_ptr(), pws.data_ptr(), pws.numel(), s), "hicgat_gat_param_grads")
+        return dxl, datt_l.view(ctx.att_shape), datt_r.view(ctx.att_shape), dbias, None, None, None, None
+
+
 def _glorot_(t: torch.Tensor) -> None:
     s = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
     with torch.no_grad():
@@ -149,6 +199,9 @@ class GATConv(nn.Module):
         if not concat or dropout != 0.0 or not add_self_loops or not bias:
             raise NotImplementedError("only the configuration the reference uses: concat=True, dropout=0, add_self_loops=True, bias=True")
         self.in_channels, self.out_channels, self.heads, self.negative_slope = in_channels, out_channels, heads, negative_slope
+        # message-passing path: "auto" = dense tiles when >= dense_threshold of all pairs are edges
+        # (and the kernels support the shape), else the CSR warp-per-row kernels; "csr" / "dense" force one
+        self.path, self.dense_threshold, self.dense_max_n = "auto", 0.35, 32768
         self.lin_l = nn.Linear(in_channels, heads * out_channels, bias=False)
         self.lin_r = self.lin_l
         self.att_l = nn.Parameter(torch.empty(1, heads, out_channels))
@@ -167,7 +220,12 @@ class GATConv(nn.Module):
     def forward(self, x, edge_index, edge_weight=None, size=None):
         graph = as_graph(edge_index, edge_weight, x.shape[0])
         xl = self.lin_l(x)
-        return _GatAttend.apply(xl, self.att_l, self.att_r, self.bias, graph, self.heads, self.out_channels, self.negative_slope)
+        dense_ok = self.out_channels % 128 == 0 and self.heads in (1, 2, 4) and graph.n <= self.dense_max_n
+        use_dense = self.path == "dense" or (self.path == "auto" and dense_ok and graph.n >= 256 and graph.density() >= self.dense_threshold)
+        if use_dense and not dense_ok:
+            raise RuntimeError("dense GAT path: channels must be a multiple of 128 and heads in {1,2,4}")
+        fn = _GatAttendDense if use_dense else _GatAttend
+        return fn.apply(xl, self.att_l, self.att_r, self.bias, graph, self.heads, self.out_channels, self.negative_slope)
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})"

@@ -205,6 +205,37 @@ HICGAT_API int hicgat_gat_bwd(const int32_t* rowptr, const int32_t* col, const i
                    float* datt_r, float* dbias, void* workspace, size_t workspace_bytes,
                    hicgat_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * (1d) Dense-tile path of the same GATConv for near-dense graphs (1 Mb / 100 kb maps): per head the
+ * attention matrix is regenerated tile by tile from the rank-1 logits, the row statistics and a
+ * bit mask of the pattern and fed to register-tiled fp32 GEMMs; nothing of size N x N is stored.
+ * Same results as hicgat_gat_fwd / _bwd up to fp32 summation order.  channels % 128 == 0.
+ *   logits      : a_src/a_dst [n,H] = <xl, att_l>, <xl, att_r> per head (shared with the CSR path)
+ *   build_mask  : mask u32[n][ceil(n/32)] from the self-loop CSR pattern (once per graph)
+ *   fwd         : out [n,H*C]; row max / 1/sum stay in `workspace` for the backward
+ *   bwd         : dxl [n,H*C], d_a_src/d_a_dst [n,H] (inputs: the forward's workspace, out, g)
+ *   param_grads : datt_l/datt_r/dbias [H*C] from d_a_src/d_a_dst (shared with the CSR path)
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API int hicgat_gat_logits(int64_t n, int heads, int channels, const float* xl, const float* att_l,
+                      const float* att_r, float* a_src, float* a_dst, hicgat_stream_t stream);
+HICGAT_API size_t hicgat_gat_dense_mask_words(int64_t n);
+HICGAT_API int hicgat_gat_dense_build_mask(const int32_t* rowptr, const int32_t* col, int64_t n, uint32_t* mask,
+                                hicgat_stream_t stream);
+HICGAT_API size_t hicgat_gat_dense_workspace_bytes(int64_t n, int heads, int channels);
+HICGAT_API int hicgat_gat_dense_fwd(const int32_t* rowptr, const int32_t* col, const uint32_t* mask, int64_t n, int heads,
+                         int channels, const float* xl, const float* a_src, const float* a_dst,
+                         const float* bias, float slope, float* out, void* workspace,
+                         size_t workspace_bytes, hicgat_stream_t stream);
+HICGAT_API int hicgat_gat_dense_bwd(const uint32_t* mask, int64_t n, int heads, int channels, const float* xl,
+                         const float* a_src, const float* a_dst, const float* att_l, const float* att_r,
+                         const float* bias, float slope, const float* out, const float* gout, float* dxl,
+                         float* d_a_src, float* d_a_dst, void* workspace, size_t workspace_bytes,
+                         hicgat_stream_t stream);
+HICGAT_API size_t hicgat_gat_param_grads_workspace_bytes(int64_t n, int heads, int channels);
+HICGAT_API int hicgat_gat_param_grads(int64_t n, int heads, int channels, const float* xl, const float* gout,
+                           const float* d_a_src, const float* d_a_dst, float* datt_l, float* datt_r,
+                           float* dbias, void* workspace, size_t workspace_bytes, hicgat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

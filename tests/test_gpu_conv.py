@@ -69,12 +69,16 @@ def _gat_case(n, density, min_kink_gap=2e-6):
     raise AssertionError("no kink-safe seed found")
 
 
+@pytest.mark.parametrize("path", ["csr", "dense"])
 @pytest.mark.parametrize("n,density,dense", [(58, 1.0, False), (114, 1.0, False), (300, 0.2, False), (700, 0.95, True), (1500, 0.5, True)])
-def test_gat_forward_backward(n, density, dense):
+def test_gat_forward_backward(n, density, dense, path):
+    """Both message-passing paths (CSR warp-per-row, dense tiles) against the oracle, including
+    sizes that are not multiples of the 64 x 128 tile and a sparse pattern through the dense path."""
     from hic_gnn_b200 import layers as glayers
 
     x, odata, gdata, oc = _gat_case(n, density)
     gc = glayers.GATConv(512, 256, heads=2).cuda()
+    gc.path = path
     gc.load_state_dict(oc.state_dict())
     assert list(gc.state_dict().keys()) == ["att_l", "att_r", "bias", "lin_l.weight", "lin_r.weight"]
     xo = x.clone().requires_grad_(True)
