@@ -23,25 +23,33 @@ constexpr int BM = 64, BN = 128, BK = 16;   // CTA tile (rows x cols) and k-step
 constexpr int TM = 8, TN = 8;               // per-thread outputs: rows {ty*4..+3, 32+ty*4..+3}, cols {tx*4..+3, 64+tx*4..+3}
 constexpr int kThreads = (BM / TM) * (BN / TN);  // 8 x 16 = 128
 
+template <int BM_>
 struct Tiles {
-    float a[2][BK][BM];
+    float a[2][BK][BM_];
     float b[2][BK][BN];
 };
 
 __device__ __forceinline__ float lrelu(float z, float slope) { return z > 0.f ? z : z * slope; }
 
-// acc[r][c] += sum_k a[k][row(r)] * b[k][col(c)] over one staged k-step
-__device__ __forceinline__ void mma_step(float (&acc)[TM][TN], const float (*__restrict__ as)[BM], const float (*__restrict__ bs)[BN], int ty, int tx) {
+// acc[r][c] += sum_k a[k][row(r)] * b[k][col(c)] over one staged k-step.  BM_ = 64: 8 rows per thread
+// {ty*4..+3, 32+ty*4..+3}; BM_ = 32: 4 rows per thread {ty*4..+3}.  Columns {tx*4..+3, 64+tx*4..+3}.
+template <int BM_>
+__device__ __forceinline__ void mma_step(float (&acc)[BM_ / 8][TN], const float (*__restrict__ as)[BM_], const float (*__restrict__ bs)[BN], int ty, int tx) {
+    constexpr int TM_ = BM_ / 8;
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
+        float a[TM_];
         const float4 a0 = *reinterpret_cast<const float4*>(&as[k][ty * 4]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&as[k][32 + ty * 4]);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+        if constexpr (TM_ == 8) {
+            const float4 a1 = *reinterpret_cast<const float4*>(&as[k][32 + ty * 4]);
+            a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        }
         const float4 b0 = *reinterpret_cast<const float4*>(&bs[k][tx * 4]);
         const float4 b1 = *reinterpret_cast<const float4*>(&bs[k][64 + tx * 4]);
-        const float a[TM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         const float b[TN] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int r = 0; r < TM; ++r)
+        for (int r = 0; r < TM_; ++r)
 #pragma unroll
             for (int c = 0; c < TN; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
     }
@@ -62,7 +70,7 @@ struct DenseArgs {
 
 // attention weight a_ij (normalised) for head h; bit = edge present
 __device__ __forceinline__ float att_weight(bool bit, float asj, float adi, float mx, float inv, float slope) {
-    return bit ? expf(lrelu(asj + adi, slope) - mx) * inv : 0.f;
+    return bit ? __expf(lrelu(asj + adi, slope) - mx) * inv : 0.f;  // argument <= 0: ex2.approx, rel. error ~5e-7
 }
 
 // ------------------------------------------------------------------ row statistics (CSR, warp per row)
@@ -108,10 +116,11 @@ __global__ void __launch_bounds__(256) mask_from_csr_kernel(const int32_t* __res
 // ------------------------------------------------------------------ generated attention tiles
 // A-tile of P (rows = targets i, k = sources j):      as[k][m] = a_{i0+m, j0+k}           (fwd)
 // A-tile of P^T (rows = sources j, k = targets i):    as[k][m] = a_{i0'+k, j0'+m}         (bwd-2)
-// thread t fills row m = t % 64 for k in {8*(t/64) .. +7}
-template <bool TRANSPOSED>
-__device__ __forceinline__ void gen_att_tile(float (*__restrict__ as)[BM], const DenseArgs& A, int h, int m0, int k0, int t) {
-    const int m = t & 63, kb = (t >> 6) * 8;
+// thread t fills row m = t % BM_ for the k-group t / BM_ (BK * BM_ / 128 consecutive k)
+template <bool TRANSPOSED, int BM_>
+__device__ __forceinline__ void gen_att_tile(float (*__restrict__ as)[BM_], const DenseArgs& A, int h, int m0, int k0, int t) {
+    constexpr int KG = BK * BM_ / kThreads;  // 8 (BM_ = 64) or 4 (BM_ = 32) sources per thread
+    const int m = t % BM_, kb = (t / BM_) * KG;
     const int gm = m0 + m;  // fwd: target i ; transposed: source j
     float fixed_s = 0.f, fixed_d = 0.f, mx = 0.f, inv = 0.f;
     uint32_t bits = 0;
@@ -119,11 +128,11 @@ __device__ __forceinline__ void gen_att_tile(float (*__restrict__ as)[BM], const
         if (!TRANSPOSED) { fixed_d = A.a_dst[gm * A.H + h]; mx = A.rmax[gm * A.H + h]; inv = A.rinv[gm * A.H + h]; }
         else fixed_s = A.a_src[gm * A.H + h];
         // the pattern is symmetric (set_diag of a symmetrised map): bit (gm, gk) serves both orientations
-        const int gk0 = k0 + kb;
-        if (gk0 < A.n) bits = (A.mask[(size_t)gm * A.words + (gk0 >> 5)] >> (gk0 & 31)) & 0xffu;  // k0, kb multiples of 8
+        const int gk0 = k0 + kb;  // multiple of KG: the KG bits sit inside one mask word
+        if (gk0 < A.n) bits = (A.mask[(size_t)gm * A.words + (gk0 >> 5)] >> (gk0 & 31)) & ((1u << KG) - 1u);
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < KG; ++q) {
         const int gk = k0 + kb + q;
         float v = 0.f;
         if (gk < A.n && ((bits >> q) & 1u)) {
@@ -150,25 +159,26 @@ __device__ __forceinline__ void store_rows_tile(float (*__restrict__ bs)[BN], co
 
 // out[i, h*C + c] = sum_j a_ij xl[j, h*C + c] + bias          (TRANSPOSED = false, X = xl)
 // dxl[j, h*C + c] = sum_i a_ij g[i, h*C + c] + d_a_src[j] att_l[c] + d_a_dst[j] att_r[c]   (TRANSPOSED = true, X = g)
-template <bool TRANSPOSED>
+template <bool TRANSPOSED, int BM_>
 __global__ void __launch_bounds__(kThreads) gat_dense_spmm_kernel(const DenseArgs A, const float* __restrict__ X, const float* __restrict__ v0,
                                                                   const float* __restrict__ v1, const float* __restrict__ s0,
                                                                   const float* __restrict__ s1, float* __restrict__ out) {
-    __shared__ __align__(16) Tiles T;
+    constexpr int TM_ = BM_ / 8;
+    __shared__ __align__(16) Tiles<BM_> T;
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
     const int F = A.H * A.C;
     const int ctiles = A.C / BN;                 // column tiles per head
     const int h = blockIdx.y / ctiles, c0 = h * A.C + (blockIdx.y % ctiles) * BN;
-    const int m0 = blockIdx.x * BM;
-    float acc[TM][TN];
+    const int m0 = blockIdx.x * BM_;
+    float acc[TM_][TN];
 #pragma unroll
-    for (int r = 0; r < TM; ++r)
+    for (int r = 0; r < TM_; ++r)
 #pragma unroll
         for (int c = 0; c < TN; ++c) acc[r][c] = 0.f;
 
     float4 breg[4];
     const int ksteps = (A.n + BK - 1) / BK;
-    gen_att_tile<TRANSPOSED>(T.a[0], A, h, m0, 0, t);
+    gen_att_tile<TRANSPOSED, BM_>(T.a[0], A, h, m0, 0, t);
     load_rows_tile(breg, X, F, A.n, 0, c0, t);
     store_rows_tile(T.b[0], breg, t);
     __syncthreads();
@@ -176,16 +186,16 @@ __global__ void __launch_bounds__(kThreads) gat_dense_spmm_kernel(const DenseArg
         const int cur = ks & 1, nxt = cur ^ 1;
         const bool more = ks + 1 < ksteps;
         if (more) load_rows_tile(breg, X, F, A.n, (ks + 1) * BK, c0, t);   // in flight during the FMAs
-        mma_step(acc, T.a[cur], T.b[cur], ty, tx);
+        mma_step<BM_>(acc, T.a[cur], T.b[cur], ty, tx);
         if (more) {
-            gen_att_tile<TRANSPOSED>(T.a[nxt], A, h, m0, (ks + 1) * BK, t);
+            gen_att_tile<TRANSPOSED, BM_>(T.a[nxt], A, h, m0, (ks + 1) * BK, t);
             store_rows_tile(T.b[nxt], breg, t);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int r = 0; r < TM; ++r) {
-        const int gm = m0 + out_row(ty, r);
+    for (int r = 0; r < TM_; ++r) {
+        const int gm = m0 + (TM_ == 8 ? out_row(ty, r) : ty * 4 + r);
         if (gm >= A.n) continue;
         float e0 = 0.f, e1 = 0.f;
         if (TRANSPOSED) { e0 = s0[gm * A.H + h]; e1 = s1[gm * A.H + h]; }
@@ -252,7 +262,7 @@ __device__ __forceinline__ void store_kmajor(float (*__restrict__ s)[LD], const 
 __global__ void __launch_bounds__(kThreads) gat_dense_bwd_logits_kernel(const DenseArgs A, const float* __restrict__ g, const float* __restrict__ xl,
                                                                         const float* __restrict__ rowdot, float* __restrict__ rowpart,
                                                                         float* __restrict__ colpart) {
-    __shared__ __align__(16) Tiles T;
+    __shared__ __align__(16) Tiles<BM> T;
     __shared__ float red_row[BM][16 + 1];   // per output row: 16 tx partials
     __shared__ float red_col[BN][8 + 1];    // per output col: 8 ty partials
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -277,7 +287,7 @@ __global__ void __launch_bounds__(kThreads) gat_dense_bwd_logits_kernel(const De
             load_kmajor<BM>(areg, g, F, A.n, i0, h * A.C + (ks + 1) * BK, t);
             load_kmajor<BN>(breg, xl, F, A.n, j0, h * A.C + (ks + 1) * BK, t);
         }
-        mma_step(acc, T.a[cur], T.b[cur], ty, tx);
+        mma_step<BM>(acc, T.a[cur], T.b[cur], ty, tx);
         if (more) {
             store_kmajor<BM, BM>(T.a[nxt], areg, t);
             store_kmajor<BN, BN>(T.b[nxt], breg, t);
@@ -305,7 +315,7 @@ __global__ void __launch_bounds__(kThreads) gat_dense_bwd_logits_kernel(const De
                     float dz = 0.f;
                     if (gj < A.n && ((bits >> q) & 1u)) {
                         const float z = A.a_src[gj * A.H + h] + adi;
-                        const float a = expf(lrelu(z, A.slope) - mx) * inv;
+                        const float a = __expf(lrelu(z, A.slope) - mx) * inv;
                         const float de = a * (acc[r][c] - rd);
                         dz = z > 0.f ? de : de * A.slope;
                     }
@@ -413,8 +423,12 @@ extern "C" int hicgat_gat_dense_fwd(const int32_t* rowptr, const int32_t* col, c
     }
     HICGAT_CHECK_LAUNCH("gat_row_stats_kernel");
     DenseArgs A{(int)n, heads, channels, L.words, mask, a_src, a_dst, rmax, rinv, slope};
-    dim3 grid((unsigned)L.ntm, (unsigned)(heads * (channels / BN)));
-    gat_dense_spmm_kernel<false><<<grid, kThreads, 0, stream>>>(A, xl, bias, nullptr, nullptr, nullptr, out);
+    const unsigned ytiles = (unsigned)(heads * (channels / BN));
+    if ((int64_t)L.ntm * ytiles >= 4 * 148) {  // enough 64-row tiles to fill the machine
+        gat_dense_spmm_kernel<false, 64><<<dim3((unsigned)L.ntm, ytiles), kThreads, 0, stream>>>(A, xl, bias, nullptr, nullptr, nullptr, out);
+    } else {                                   // small maps: 32-row tiles double the CTA count
+        gat_dense_spmm_kernel<false, 32><<<dim3((unsigned)((n + 31) / 32), ytiles), kThreads, 0, stream>>>(A, xl, bias, nullptr, nullptr, nullptr, out);
+    }
     HICGAT_CHECK_LAUNCH("gat_dense_spmm_kernel<fwd>");
     return HICGAT_OK;
 }
@@ -451,8 +465,12 @@ extern "C" int hicgat_gat_dense_bwd(const uint32_t* mask, int64_t n, int heads, 
     const int nH = (int)n * heads;
     gat_dense_reduce_partials_kernel<<<(nH + 255) / 256, 256, 0, stream>>>(rowpart, colpart, nH, L.ntn, L.ntm, d_a_dst, d_a_src);
     HICGAT_CHECK_LAUNCH("gat_dense_reduce_partials_kernel");
-    dim3 g2((unsigned)L.ntm, (unsigned)(heads * (channels / BN)));
-    gat_dense_spmm_kernel<true><<<g2, kThreads, 0, stream>>>(A, gout, att_l, att_r, d_a_src, d_a_dst, dxl);
+    const unsigned ytiles = (unsigned)(heads * (channels / BN));
+    if ((int64_t)L.ntm * ytiles >= 4 * 148) {
+        gat_dense_spmm_kernel<true, 64><<<dim3((unsigned)L.ntm, ytiles), kThreads, 0, stream>>>(A, gout, att_l, att_r, d_a_src, d_a_dst, dxl);
+    } else {
+        gat_dense_spmm_kernel<true, 32><<<dim3((unsigned)((n + 31) / 32), ytiles), kThreads, 0, stream>>>(A, gout, att_l, att_r, d_a_src, d_a_dst, dxl);
+    }
     HICGAT_CHECK_LAUNCH("gat_dense_spmm_kernel<bwd>");
     return HICGAT_OK;
 }
