@@ -214,7 +214,11 @@ __global__ void __launch_bounds__(256) gat_bwd_edge_kernel(const int32_t* __rest
     float dotsum[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) dotsum[h] = 0.f;
-    // pass 1: da_k for every entry (all lanes cooperate on one entry; 2 entries in flight)
+    // pass 1: da_k = <g_i, xl_j>_head for every entry.  Four entries at a time: each lane holds its
+    // 16-channel partial of 4 x H dot products, which are reduced across the warp by a
+    // transpose-reduce butterfly (4 -> 2 -> 1 values over xor 16 / 8, then xor 4 / 2 / 1): 6 shuffles
+    // per head per 4 entries instead of 20, plus one shuffle to hand each sum to the lane that owns
+    // the entry.
     for (int base = rs; base < re; base += 32) {
         const int k = base + lane;
         const int myj = k < re ? col[k] : 0;
@@ -222,31 +226,43 @@ __global__ void __launch_bounds__(256) gat_bwd_edge_kernel(const int32_t* __rest
         float myda[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) myda[h] = 0.f;
-        for (int t = 0; t < cnt; t += 2) {
-            float4 v[2][Q];
-            int j[2];
+        for (int t = 0; t < cnt; t += 4) {
+            float4 v[4][Q];
+            int j[4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) j[u] = __shfl_sync(0xffffffffu, myj, (t + u) & 31);
+            for (int u = 0; u < 4; ++u) j[u] = __shfl_sync(0xffffffffu, myj, (t + u) & 31);
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < 4; ++u) {
                 if (t + u < cnt) {
 #pragma unroll
                     for (int q = 0; q < Q; ++q) v[u][q] = ldg_f4(xl + (size_t)j[u] * F + q * 128 + lane * 4);
                 }
+            }
+            float part[4][H];
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) part[u][h] = 0.f;
                 if (t + u < cnt) {
-                    float part[H];
 #pragma unroll
-                    for (int h = 0; h < H; ++h) part[h] = 0.f;
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) part[q / QH] += dot4(g[q], v[u][q]);
-#pragma unroll
-                    for (int h = 0; h < H; ++h) {
-                        const float d = warp_sum(part[h]);
-                        if (lane == t + u) myda[h] = d;
-                    }
+                    for (int q = 0; q < Q; ++q) part[u][q / QH] += dot4(g[q], v[u][q]);
                 }
+            }
+            const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+            const int e = lane - t;  // entry of this group owned by this lane (valid for 0 <= e < 4)
+            const int src = ((e >> 1) & 1) << 4 | (e & 1) << 3;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                // entries {0,1} end up in lanes with bit 4 clear, {2,3} in lanes with bit 4 set
+                float w0 = (up16 ? part[2][h] : part[0][h]) + __shfl_xor_sync(0xffffffffu, up16 ? part[0][h] : part[2][h], 16);
+                float w1 = (up16 ? part[3][h] : part[1][h]) + __shfl_xor_sync(0xffffffffu, up16 ? part[1][h] : part[3][h], 16);
+                float x = (up8 ? w1 : w0) + __shfl_xor_sync(0xffffffffu, up8 ? w0 : w1, 8);
+                x += __shfl_xor_sync(0xffffffffu, x, 4);
+                x += __shfl_xor_sync(0xffffffffu, x, 2);
+                x += __shfl_xor_sync(0xffffffffu, x, 1);
+                const float d = __shfl_sync(0xffffffffu, x, src & 31);
+                if (e >= 0 && e < 4) myda[h] = d;
+            }
         }
         if (k < re) {
 #pragma unroll
