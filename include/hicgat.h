@@ -236,6 +236,17 @@ HICGAT_API int hicgat_gat_param_grads(int64_t n, int heads, int channels, const 
                            const float* d_a_src, const float* d_a_dst, float* datt_l, float* datt_r,
                            float* dbias, void* workspace, size_t workspace_bytes, hicgat_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * (next row f-1) Knight-Ruiz balancing, the step before load_input (r_utils.R:1-93 through
+ * normalize.R:1-11, an R subprocess at HiC-GNN_main.py:85): the two O(N^2) pieces.
+ *   gemv           : y = A x, f64, row-major, fixed reduction order (r_utils.R:24,38,66)
+ *   kr_scale_round : out = round(x_i A_ij x_j, decimals) (r_utils.R:75,90)
+ * The Newton-CG control flow lives in hic_gnn_b200/kr.py.
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API int hicgat_gemv_f64(const double* A, int64_t ld, int64_t n, const double* x, double* y, hicgat_stream_t stream);
+HICGAT_API int hicgat_kr_scale_round_f64(const double* A, int64_t ld, int64_t n, const double* x, double* out, int64_t ldo,
+                              int decimals, hicgat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

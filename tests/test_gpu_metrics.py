@@ -1,0 +1,59 @@
+"""GPU dSCC / Pearson against scipy, and the north_star's "within 1e-3 on final dSCC": the CUDA loop
+and the oracle loop, run with the reference's own stop rule from the same state_dict on the
+shipped chr19 1 Mb map, must end at the same dSCC."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import random_coords, small_map, wish_from_map
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,density", [(58, 1.0), (300, 0.2), (700, 0.6)])
+def test_dscc_and_pearson_match_scipy(n, density):
+    from scipy.stats import pearsonr, spearmanr
+
+    from hic_gnn_b200 import metrics
+    from oracle import loss as oloss
+
+    truth = wish_from_map(small_map(n, density, seed=3), 1.0)  # many exact ties at 1.0 when sparse
+    coords = random_coords(n, seed=4)
+    dist_truth, dist_out = oloss.triu_pairs(truth, coords)
+    want_s = spearmanr(dist_truth.numpy(), dist_out.numpy())[0]
+    want_p = pearsonr(dist_truth.numpy(), dist_out.numpy())[0]
+    assert abs(metrics.dscc(coords.cuda(), truth.cuda()) - want_s) < 1e-6
+    assert abs(metrics.pearson(coords.cuda(), truth.cuda()) - want_p) < 1e-6
+    ranks = metrics.average_ranks(dist_truth.cuda())
+    from scipy.stats import rankdata
+
+    assert np.array_equal(ranks.cpu().numpy(), rankdata(dist_truth.numpy(), method="average"))
+
+
+@pytest.mark.parametrize("cls,mode", [("Net", "mse"), ("GATNetSelectiveResidualsUpdated", "mse_pearson")])
+def test_final_dscc_within_1e3_of_oracle_on_chr19(golden, cls, mode):
+    from hic_gnn_b200 import metrics, models as gmodels, train as gtrain, utils as gutils
+    from oracle import graph as ograph, loop as oloop, loss as oloss, models as omodels, wish as owish
+
+    g, _ = golden
+    adj = g["1mb_kr_oracle"]  # GM12878 chr19 1 Mb after KR (Data/GM12878_1mb_chr19_list.txt)
+    n = adj.shape[0]
+    gen = torch.Generator().manual_seed(7)
+    x = 0.25 * torch.randn(n, 512, generator=gen)
+    odata = ograph.load_input(adj.copy(), x.numpy())
+    gdata = gutils.load_input(adj.copy(), x.numpy())
+    truth = owish.cont2dist(odata.y.clone(), 1.0)
+    torch.manual_seed(42)
+    om = getattr(omodels, cls)()
+    init = {k: v.clone() for k, v in om.state_dict().items()}
+    # reference loop: while abs(old - new) > 1e-8 (HiC-GNN_main.py:123-131)
+    h_o, _ = oloop.train(om, odata.x.float(), odata.edge_index, truth, mode=mode, lr=1e-3, thresh=1e-8, max_steps=4000, as_written=False)
+    want = oloss.dscc(om.get_model(odata.x.float(), odata.edge_index).detach(), truth)
+    gm = getattr(gmodels, cls)().cuda()
+    gm.load_state_dict(init)
+    target = gutils.wish_target(gdata.y, 1.0)
+    h_g = gtrain.fit(gm, gdata.x.float(), gdata.edge_index, target, mode=mode, lr=1e-3, thresh=1e-8, max_steps=4000)
+    with torch.no_grad():
+        got = metrics.dscc(gm.get_model(gdata.x.float(), gdata.edge_index), target)
+    assert abs(got - want) < 1e-3, (got, want, len(h_g), len(h_o))
+    assert abs(h_g[-1] - h_o[-1]) / abs(h_o[-1]) < 1e-2
