@@ -144,3 +144,16 @@ def test_cont2dist_zero_contacts_and_row_blocks():
         _, t = ops.cont2dist(a[r0:r1].contiguous(), 1.0, want_f64=False, want_f32=True, r0=r0, r1=r1, max_reduce=lambda m: m.fill_(float(true_max)))
         blocks.append(t.dense())
     assert torch.equal(torch.cat(blocks).cpu(), want.float())
+
+
+@pytest.mark.parametrize("tag", ["1mb", "500kb", "dup"])
+def test_convert_to_matrix_matches_reference_golden(golden, tag):
+    """Row f-2: contact list -> dense matrix on the GPU, against the reference's own
+    utils.convert_to_matrix outputs (golden) incl. duplicate records ("last record wins")."""
+    from hic_gnn_b200 import utils
+
+    g, _ = golden
+    if f"{tag}_list" not in g:
+        pytest.skip("no list fixture for this tag")
+    got = utils.convert_to_matrix(g[f"{tag}_list"]).cpu().numpy()
+    assert np.array_equal(got, g[f"{tag}_matrix"])
