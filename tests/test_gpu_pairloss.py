@@ -59,7 +59,10 @@ def test_mse_random_maps(n, density):
     coords = random_coords(n, seed=n + 1)
     want_l, want_g = _oracle_mse(coords, truth)
     got_l, got_g, _ = _gpu_loss(coords, truth, "mse")
-    assert abs(float(got_l) - float(want_l)) <= TOL * max(float(want_l), 1e-12)
+    # relative to the loss, but never tighter than 1e-5 of 1e-3 * mean(t^2): with one or three pairs the
+    # random coordinates can land on d ~ t, where the loss is a cancellation of two f32 distances
+    floor = 1e-3 * float((truth.float() ** 2).mean())
+    assert abs(float(got_l) - float(want_l)) <= TOL * max(float(want_l), floor, 1e-12)
     if n > 1:
         assert rel_err(got_g, want_g) < TOL
 
