@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"], help="exchange of the sharded loss partials")
     ap.add_argument("--emulate-world", type=int, default=0, help="profiling aid: on ONE GPU run rank 0's row block of a W-way split (not a bench line)")
     ap.add_argument("--no-measure-copy", dest="measure_copy", action="store_false", help="skip the same-process copy-bandwidth control")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="run the single-GPU training step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -425,6 +426,31 @@ def run_native(args):
                "note": "per rank: coords + this rank's f32 target rows from pinned host memory every step (PCIe-bound by construction)"}
         del host_target, hp
         torch.cuda.empty_cache()
+        # (2b) the training-loop variant of the same call: the target stays resident (uploaded once, like
+        # utils.wish_target does), only the step's coordinates go up and its loss moments + gradient come back
+        out_host = torch.empty(N.PAIR_NMOM + 3 * n, dtype=torch.float64, pin_memory=True)
+        coords_dev = torch.empty_like(coords)
+
+        def resident_step():
+            coords_dev.copy_(host_coords, non_blocking=True)
+            m_, g_ = loss_fn(coords_dev)
+            out_host[: N.PAIR_NMOM].copy_(m_, non_blocking=True)
+            out_host[N.PAIR_NMOM:].copy_(g_.reshape(-1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        cursor["k"] = None
+        for _ in range(3):
+            resident_step()
+        barrier()
+        start.record()
+        for _ in range(K):
+            resident_step()
+        stop.record()
+        barrier()
+        r_ms = max_over_ranks(start.elapsed_time(stop))
+        e2e["resident_target"] = {"value": float(n) * float(n) * K / (r_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": r_ms / K,
+                                  "h2d_bytes_per_step": int(host_coords.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 8),
+                                  "note": "same call with the f32 target resident in HBM (how the training loop uses it): per step coords H2D, moments+gradient D2H, host sync"}
 
     # ---- (3) whole training step: GAT net forward, fused loss, backward, Adam
     train_out = None
@@ -434,7 +460,8 @@ def run_native(args):
         model = models.GATNetSelectiveResidualsUpdated().to(dev)
         x = synth.synthetic_features(n, device=dev)
         reducer = ops.sharded_reducer(target, "mse_moments", transport=args.transport) if world > 1 else None
-        tstep = train.TrainStep(model, x, graph, target, mode="mse_pearson", lr=1e-3, use_cuda_graph=False, reducer=reducer)
+        graphed = world == 1 and not args.no_cuda_graph  # the sharded step holds a per-step epoch argument: eager
+        tstep = train.TrainStep(model, x, graph, target, mode="mse_pearson", lr=1e-3, use_cuda_graph=graphed, reducer=reducer)
         for _ in range(3):
             total, _m = tstep()
         barrier()
@@ -453,7 +480,7 @@ def run_native(args):
         t_ms = max_over_ranks(start.elapsed_time(stop))
         train_out = {"steps_per_s": Kt / (t_ms * 1e-3), "ms_per_step": t_ms / Kt, "steps": Kt, "model": "GATNetSelectiveResidualsUpdated",
                      "loss": "mse + alpha*(1-pearson)", "nnz": graph.nnz, "total_loss": float(total),
-                     "hicgat_launches_per_step": (N.launch_count() - l0) / Kt, "gnn": "replicated", "loss_rows": "sharded" if world > 1 else "all"}
+                     "hicgat_launches_per_step": (N.launch_count() - l0) / Kt, "gnn": "replicated", "loss_rows": "sharded" if world > 1 else "all", "cuda_graph": graphed}
         del tstep, model, x
     sampler.stop()
 
