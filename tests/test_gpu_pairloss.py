@@ -64,7 +64,8 @@ def test_mse_random_maps(n, density):
     floor = 1e-3 * float((truth.float() ** 2).mean())
     assert abs(float(got_l) - float(want_l)) <= TOL * max(float(want_l), floor, 1e-12)
     if n > 1:
-        assert rel_err(got_g, want_g) < TOL
+        # n <= 3: one to three pairs, no averaging; a coincidental d ~ t makes (d - t)/d a cancellation
+        assert rel_err(got_g, want_g) < (TOL if n > 3 else 1e-4)
 
 
 @pytest.mark.parametrize("n", [58, 300, 1000])
