@@ -226,3 +226,50 @@ def test_full_size_closed_form_properties(n):
     assert abs(float((g.double() * y.double()).sum()) - 2 * (s - 1) * mean_t2) / (2 * (s - 1) * mean_t2) < TOL
     assert abs(float(pearson_from_moments(m, n * (n - 1) / 2)) - 1.0) < 1e-6
     assert abs(float(g.double().sum(0).abs().max())) < 1e-6  # translation invariance: sum_i grad_i = 0
+
+
+def test_full_size_c5_properties_and_row_sharding():
+    """BASELINE.json's largest configuration (49 850 loci, 2.5e9 ordered pairs, 9.9 GB f32 target) through
+    size-independent properties: target = pairwise distances of points y; coords = y gives loss 0 and gradient
+    0; coords = s*y gives MSE = (s-1)^2 mean(t^2), <grad, y> = 2 (s-1) mean(t^2), Pearson r = 1 and a
+    translation-free gradient; and the 8 row blocks of an 8-GPU run add up to the full-matrix launch."""
+    import hic_gnn_b200 as hg
+    from hic_gnn_b200 import ops, sharding
+    from hic_gnn_b200.ops import pearson_from_moments
+
+    n = 49850
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~25 GB of device memory")
+    y = random_coords(n, seed=21).cuda()
+    tgt = hg.WishTarget.empty(n)
+    for r0 in range(0, n, 4096):  # target rows = exact f32 distances of y, written block-wise
+        r1 = min(r0 + 4096, n)
+        tgt.data[r0:r1, :n] = torch.cdist(y[r0:r1].double(), y.double()).float()
+    tgt.data[:, :n].fill_diagonal_(0)
+    mean_t2 = 0.0
+    for r0 in range(0, n, 4096):
+        mean_t2 += float((tgt.data[r0:r0 + 4096, :n].double() ** 2).sum())
+    mean_t2 /= float(n) * float(n)
+    loss0, _ = hg.pairwise_loss(y.clone().requires_grad_(True), tgt, "mse_moments")
+    assert float(loss0) < 1e-12 * mean_t2 + 1e-14
+    s = 1.25
+    c = (s * y).requires_grad_(True)
+    loss, m = hg.pairwise_loss(c, tgt, "mse_moments")
+    (g,) = torch.autograd.grad(loss, c)
+    want = (s - 1) ** 2 * mean_t2
+    assert abs(float(loss) - want) / want < TOL
+    assert abs(float((g.double() * y.double()).sum()) - 2 * (s - 1) * mean_t2) / (2 * (s - 1) * mean_t2) < TOL
+    assert abs(float(pearson_from_moments(m, n * (n - 1) / 2)) - 1.0) < 1e-6
+    assert float(g.double().sum(0).abs().max()) < 1e-6 * float(g.abs().max()) * n
+    # row blocks of an 8-way split, each through its own launch (what 8 ranks compute), against the full launch
+    mode = ops._MODES["mse_moments_full"]
+    m_full, g_full = ops.pairloss_raw(c.detach(), tgt, mode, 4.0 / n**2, 0.0)
+    m_sum, g_sum = torch.zeros_like(m_full), torch.zeros(n, 3, dtype=torch.float64, device="cuda")
+    for rank in range(8):
+        r0, r1 = sharding.row_block(n, rank, 8)
+        blk = hg.WishTarget(tgt.data[r0:r1], n, r0, r1)
+        mb, gb = ops.pairloss_raw(c.detach(), blk, mode, 4.0 / n**2, 0.0)
+        m_sum += mb
+        g_sum += gb.double()
+    assert rel_err(m_sum, m_full) < 1e-7
+    assert rel_err(g_sum, g_full) < TOL
