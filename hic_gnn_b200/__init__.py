@@ -7,6 +7,6 @@ behind the C ABI of ``include/hicgat.h`` (``libhicgat_sm100.so``).  No Triton, n
 torch_geometric, no CPU fallback.
 """
 from . import _native, ops  # noqa: F401
-from .ops import WishTarget, pairwise_loss, pair_moments, pairdist  # noqa: F401
+from .ops import SparseWishTarget, WishTarget, pairwise_loss, pair_moments, pairdist  # noqa: F401
 
 __version__ = "0.1.0"

@@ -162,6 +162,7 @@ struct Params {
     int64_t pitch;
     int n, r0, r1, rb, nstrips, nchunks;  // nchunks = grid.y = chunk slots per strip (staggered strips use one more than the others)
     int stagger;                          // 1: strips with odd (strip / 148) start half a chunk early (see chunk_rows)
+    float fill;                           // implicit-target kernel: wish distance of every non-edge pair
     float c_mse, c_l1;
     double* moments;
     float* grad;
@@ -469,6 +470,170 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_ldg_kernel(const Params 
     park_warp<MODE>(a, S, warp, lane);
     __syncthreads();
     finish_cta<MODE>(P, S, strip, chunk, count, threadIdx.x, kThreads);
+}
+
+// ------------------------------------------------------------------ implicit target, dense part (compute only)
+// on a sparse map every non-edge pair has wish distance `fill` (1.0 after
+// cont2dist: zero contacts map to max/max, utils.py:78-80) and the diagonal 0, so the N x N target need
+// not exist.  This kernel evaluates the loss against that constant background with no target loads at
+// all (FP32 / MUFU bound instead of HBM bound); pairloss_csr_fix_kernel then corrects the nnz pairs
+// that do carry a contact.  Same decomposition, arithmetic and reductions as the streamed kernels.
+template <uint32_t MODE>
+__global__ void __launch_bounds__(kThreads, 2) pairloss_const_kernel(const Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_xy = reinterpret_cast<float4*>(smem_raw);                          // [rb] (x,x,y,y)
+    float2* s_z = reinterpret_cast<float2*>(smem_raw + sizeof(float4) * P.rb);   // [rb] (z,z)
+    __shared__ CombineSmem S;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x, chunk = blockIdx.y;
+    const int n = P.n;
+    const int col0 = strip * kCols + lane * 4;
+    int row_begin, nrows;
+    const int count = chunk_rows(P, strip, chunk, row_begin, nrows);
+    if (chunk >= count) return;
+    const bool edge = (strip + 1) * kCols > n;
+    for (int r = threadIdx.x; r < nrows; r += kThreads) {
+        const float* c = P.coords + (size_t)(row_begin + r) * 3;
+        float x = c[0], y = c[1], z = c[2];
+        s_xy[r] = make_float4(x, x, y, y);
+        s_z[r] = make_float2(z, z);
+    }
+    ColumnRegs c;
+    load_columns(c, P.coords, col0, n);
+    Acc a;
+    acc_zero(a);
+    __syncthreads();
+    const int strip_lo = strip * kCols, strip_hi = strip_lo + kCols - 1;
+    const int ngroups = (nrows + kU - 1) / kU;
+    const float f = P.fill;
+    for (int g = warp; g < ngroups; g += kWarps) {
+        const int rl = g * kU, rg = row_begin + rl;
+        const int rows_here = min(kU, nrows - rl);
+        float4 t[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) t[u] = make_float4(f, f, f, f);
+        if (rg + kU - 1 >= strip_lo && rg <= strip_hi) {  // the group touches the diagonal: t_ii = 0
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int dc = rg + u - col0;
+                if (dc == 0) t[u].x = 0.f;
+                if (dc == 1) t[u].y = 0.f;
+                if (dc == 2) t[u].z = 0.f;
+                if (dc == 3) t[u].w = 0.f;
+            }
+        }
+        process_group<MODE>(a, c, t, XiPtr{s_xy + rl, s_z + rl}, rows_here, rg, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1);
+    }
+    park_warp<MODE>(a, S, warp, lane);
+    __syncthreads();
+    finish_cta<MODE>(P, S, strip, chunk, count, threadIdx.x, kThreads);
+}
+
+// Correction of the pairs that carry a contact (CSR rows [r0, r1), warp per row, ROW-side sums: by the
+// symmetry of the target the row-side contribution of row i equals what the column-side sum of a
+// streamed kernel would have put on locus i over all ranks).  For edge (i, j) with wish value t:
+//   loss terms   (d - t)^2 - (d - fill)^2            gradient   c * [(d - t) - (d - fill)] / d * (x_i - x_j)
+// Moments are corrected for j > i.  Adds into grad rows [r0, r1) and writes per-CTA f64 partials that the
+// last CTA adds to `moments` in CTA order.
+template <uint32_t MODE>
+__global__ void __launch_bounds__(256) pairloss_csr_fix_kernel(const float* __restrict__ coords, const int32_t* __restrict__ rowptr,
+                                                               const int32_t* __restrict__ col, const float* __restrict__ tval, float fill, int n,
+                                                               int r0, int r1, float c_mse, float c_l1, double* __restrict__ moments,
+                                                               float* __restrict__ grad, double* __restrict__ grad64, double* __restrict__ part,
+                                                               unsigned* __restrict__ counter) {
+    __shared__ double s_m[8][kNM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = r0 + blockIdx.x * 8 + warp;
+    double m[kNM];
+#pragma unroll
+    for (int k = 0; k < kNM; ++k) m[k] = 0.0;
+    if (i < r1) {
+        const float xi = coords[(size_t)i * 3], yi = coords[(size_t)i * 3 + 1], zi = coords[(size_t)i * 3 + 2];
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        for (int k = rowptr[i] + lane; k < rowptr[i + 1]; k += 32) {
+            const int j = col[k];
+            if (j == i) continue;
+            const float t = tval[k];
+            const float dx = xi - coords[(size_t)j * 3], dy = yi - coords[(size_t)j * 3 + 1], dz = zi - coords[(size_t)j * 3 + 2];
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, 1e-30f)));
+            const float rs = rsqrt_approx(d2);
+            const float d = d2 * rs;
+            const float et = d - t, ef = d - fill;
+            const double dsee = (double)et * et - (double)ef * ef;
+            m[0] += dsee;
+            float w = 0.f;
+            if constexpr ((MODE & 3u) == HICGAT_PAIR_GRAD_MSE) w = c_mse * (fill - t) * rs;
+            else if constexpr ((MODE & 3u) == HICGAT_PAIR_GRAD_L1) w = c_l1 * (copysignf(1.f, et) - copysignf(1.f, ef)) * rs;
+            else if constexpr ((MODE & 3u) == 3u) w = (c_mse * (fill - t) + c_l1 * (copysignf(1.f, et) - copysignf(1.f, ef))) * rs;
+            gx = fmaf(w, dx, gx); gy = fmaf(w, dy, gy); gz = fmaf(w, dz, gz);
+            if constexpr ((MODE & (kMomFull | kMomLight)) != 0) {
+                if (j > i) {
+                    m[6] += (double)d * ((double)t - (double)fill);
+                    m[7] += dsee;
+                    if constexpr ((MODE & kMomFull) != 0) {
+                        m[1] += (double)fabsf(et) - (double)fabsf(ef);
+                        m[4] += (double)t - (double)fill;
+                        m[5] += (double)t * t - (double)fill * fill;
+                    }
+                }
+            }
+        }
+        if constexpr ((MODE & 3u) != 0) {
+            gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
+            if (lane == 0) {
+                if (grad) { grad[(size_t)i * 3] += gx; grad[(size_t)i * 3 + 1] += gy; grad[(size_t)i * 3 + 2] += gz; }
+                if (grad64) {  // packed layout holds f32 values widened: keep that invariant
+                    grad64[(size_t)i * 3] = (double)(float)((float)grad64[(size_t)i * 3] + gx);
+                    grad64[(size_t)i * 3 + 1] = (double)(float)((float)grad64[(size_t)i * 3 + 1] + gy);
+                    grad64[(size_t)i * 3 + 2] = (double)(float)((float)grad64[(size_t)i * 3 + 2] + gz);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kNM; ++k) m[k] = warp_sum(m[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kNM; ++k) s_m[warp][k] = m[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < kNM) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += s_m[w][threadIdx.x];
+        __stcg(part + (size_t)blockIdx.x * kNM + threadIdx.x, s);
+    }
+    __syncthreads();
+    __shared__ unsigned ticket;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        ticket = atomicAdd(counter, 1u);
+        __threadfence();
+    }
+    __syncthreads();
+    if (ticket != gridDim.x - 1) return;
+    if (threadIdx.x == 0) *counter = 0u;
+    // last CTA: add all partials to the moments in CTA order (thread t: CTAs t, t+256, ...; then lanes, warps)
+#pragma unroll
+    for (int k = 0; k < kNM; ++k) m[k] = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += 256) {
+#pragma unroll
+        for (int k = 0; k < kNM; ++k) m[k] += __ldcg(part + (size_t)b * kNM + k);
+    }
+#pragma unroll
+    for (int k = 0; k < kNM; ++k) m[k] = warp_sum(m[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kNM; ++k) s_m[warp][k] = m[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < kNM) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += s_m[w][threadIdx.x];
+        moments[threadIdx.x] += s;
+    }
 }
 
 // ------------------------------------------------------------------ variant 0: TMA + mbarrier ring
@@ -846,6 +1011,107 @@ extern "C" int hicgat_pairloss_fwd_bwd_packed(const float* coords, const float* 
         return HICGAT_ERR_INVALID;
     }
     return pairloss_impl(coords, target, pitch, n, r0, r1, mode, c_mse, c_l1, packed, nullptr, packed + HICGAT_PAIR_NMOM, workspace, workspace_bytes, stream);
+}
+
+// ------------------------------------------------------------------ implicit (sparse) target entry points
+namespace {
+struct SparseLayout {
+    Layout dense;
+    size_t off_counter, off_part, total;
+    int fix_ctas;
+};
+SparseLayout sparse_layout(int64_t n, int64_t r0, int64_t r1) {
+    SparseLayout L;
+    L.dense = make_layout(n, r0, r1, 1);  // row chunks <= 1024: the x_i staging fits the default 48 KB of shared memory
+    L.fix_ctas = (int)((r1 - r0 + 7) / 8);
+    if (L.fix_ctas < 1) L.fix_ctas = 1;
+    L.off_counter = align_up(L.dense.total, 256);
+    L.off_part = L.off_counter + 256;
+    L.total = L.off_part + sizeof(double) * kNM * (size_t)L.fix_ctas;
+    return L;
+}
+
+template <uint32_t MODE>
+cudaError_t launch_sparse(const Params& P, dim3 grid, const int32_t* rowptr, const int32_t* col, const float* tval, int fix_ctas, double* part,
+                          unsigned* counter, cudaStream_t stream) {
+    const size_t smem = (sizeof(float4) + sizeof(float2)) * (size_t)P.rb;
+    pairloss_const_kernel<MODE><<<grid, kThreads, smem, stream>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    pairloss_csr_fix_kernel<MODE><<<fix_ctas, 256, 0, stream>>>(P.coords, rowptr, col, tval, P.fill, P.n, P.r0, P.r1, P.c_mse, P.c_l1, P.moments, P.grad,
+                                                                 P.grad64, part, counter);
+    return cudaGetLastError();
+}
+}  // namespace
+
+extern "C" size_t hicgat_pairloss_sparse_workspace_bytes(int64_t n, int64_t r0, int64_t r1) {
+    if (n <= 0 || r0 < 0 || r1 < r0 || r1 > n) return 0;
+    return sparse_layout(n, r0, r1).total;
+}
+
+static int pairloss_sparse_impl(const float* coords, const int32_t* rowptr, const int32_t* col, const float* tval, float fill, int64_t n,
+                                int64_t r0, int64_t r1, uint32_t mode, float c_mse, float c_l1, double* moments, float* grad, double* grad64,
+                                void* workspace, size_t workspace_bytes, hicgat_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HICGAT_REQUIRE(n > 0 && n < (1ll << 30) && r0 >= 0 && r1 >= r0 && r1 <= n, "hicgat_pairloss_sparse_fwd_bwd: bad n/r0/r1 (%lld,%lld,%lld)", (long long)n, (long long)r0, (long long)r1);
+    HICGAT_REQUIRE(coords && rowptr && (col || r0 == r1) && (tval || r0 == r1) && moments && workspace, "hicgat_pairloss_sparse_fwd_bwd: null pointer");
+    HICGAT_REQUIRE((mode & ~31u) == 0, "hicgat_pairloss_sparse_fwd_bwd: unknown mode bits 0x%x", mode);
+    const bool ws_clean = (mode & HICGAT_PAIR_WS_CLEAN) != 0;
+    mode &= ~HICGAT_PAIR_WS_CLEAN;
+    if (mode & HICGAT_PAIR_MOMENTS) mode &= ~HICGAT_PAIR_MOMENTS_D;
+    if ((mode & HICGAT_PAIR_MOMENTS_D) && (mode & HICGAT_PAIR_GRAD_L1)) mode = (mode & ~HICGAT_PAIR_MOMENTS_D) | HICGAT_PAIR_MOMENTS;
+    HICGAT_REQUIRE(!(mode & 3u) || grad || grad64, "hicgat_pairloss_sparse_fwd_bwd: grad is NULL but a gradient mode is set");
+    const SparseLayout L = sparse_layout(n, r0, r1);
+    if (workspace_bytes < L.total) {
+        set_error("hicgat_pairloss_sparse_fwd_bwd: workspace %zu < required %zu", workspace_bytes, L.total);
+        return HICGAT_ERR_WORKSPACE;
+    }
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    if (!ws_clean) {
+        HICGAT_CUDA(cudaMemsetAsync(ws + L.dense.off_counts, 0, sizeof(unsigned) * (size_t)(L.dense.nstrips + 1), stream));
+        HICGAT_CUDA(cudaMemsetAsync(ws + L.off_counter, 0, sizeof(unsigned), stream));
+    }
+    if (r1 == r0) {
+        HICGAT_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * kNM, stream));
+        if (grad) HICGAT_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * 3 * (size_t)n, stream));
+        if (grad64) HICGAT_CUDA(cudaMemsetAsync(grad64, 0, sizeof(double) * 3 * (size_t)n, stream));
+        return HICGAT_OK;
+    }
+    Params P;
+    P.coords = coords; P.target = nullptr; P.pitch = 0;
+    P.n = (int)n; P.r0 = (int)r0; P.r1 = (int)r1; P.rb = L.dense.rb; P.nstrips = L.dense.nstrips; P.nchunks = L.dense.nchunks; P.stagger = L.dense.stagger;
+    P.fill = fill;
+    P.c_mse = c_mse; P.c_l1 = c_l1; P.moments = moments; P.grad = grad; P.grad64 = grad64;
+    P.strip_count = reinterpret_cast<unsigned*>(ws + L.dense.off_counts);
+    P.done_count = P.strip_count + L.dense.nstrips;
+    P.mpart = reinterpret_cast<double*>(ws + L.dense.off_mpart);
+    P.spart = reinterpret_cast<double*>(ws + L.dense.off_spart);
+    P.gpart = reinterpret_cast<float*>(ws + L.dense.off_gpart);
+    dim3 grid(L.dense.nstrips, L.dense.nchunks);
+    double* part = reinterpret_cast<double*>(ws + L.off_part);
+    unsigned* counter = reinterpret_cast<unsigned*>(ws + L.off_counter);
+    cudaError_t err = cudaSuccess;
+    switch (mode) {
+#define HICGAT_CASE(M) case M: err = launch_sparse<M>(P, grid, rowptr, col, tval, L.fix_ctas, part, counter, stream); break;
+        HICGAT_CASE(0u) HICGAT_CASE(1u) HICGAT_CASE(2u) HICGAT_CASE(3u) HICGAT_CASE(4u)
+        HICGAT_CASE(5u) HICGAT_CASE(6u) HICGAT_CASE(7u) HICGAT_CASE(8u) HICGAT_CASE(9u)
+#undef HICGAT_CASE
+        default:
+            set_error("hicgat_pairloss_sparse_fwd_bwd: unsupported mode 0x%x", mode);
+            return HICGAT_ERR_INVALID;
+    }
+    if (err != cudaSuccess) {
+        set_error("sparse pairloss kernel launch failed: %s", cudaGetErrorString(err));
+        return HICGAT_ERR_CUDA;
+    }
+    count_launch(2);
+    return HICGAT_OK;
+}
+
+extern "C" int hicgat_pairloss_sparse_fwd_bwd(const float* coords, const int32_t* rowptr, const int32_t* col, const float* tval, float fill,
+                                              int64_t n, int64_t r0, int64_t r1, uint32_t mode, float c_mse, float c_l1, double* moments,
+                                              float* grad, void* workspace, size_t workspace_bytes, hicgat_stream_t stream) {
+    return pairloss_sparse_impl(coords, rowptr, col, tval, fill, n, r0, r1, mode, c_mse, c_l1, moments, grad, nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int hicgat_pairdist_fwd(const float* coords, int64_t n, float* dist, int64_t pitch, hicgat_stream_t stream_) {

@@ -88,6 +88,44 @@ class WishTarget:
         return self._tmom
 
 
+class SparseWishTarget:
+    """Implicit wish-distance target of a sparse map: the symmetric,
+    diagonal-free CSR pattern of ``load_input`` with the wish distance of every stored pair;
+    all other off-diagonal pairs are ``fill`` (1.0 after ``cont2dist``: zero contacts map to
+    max/max, utils.py:78-80) and the diagonal is 0.  Rows ``[r0, r1)`` are this rank's share."""
+
+    def __init__(self, n: int, rowptr32: torch.Tensor, col32: torch.Tensor, tval: torch.Tensor, fill: float = 1.0, r0: int = 0, r1: int | None = None):
+        _cuda(rowptr32, col32, tval)
+        assert rowptr32.dtype == torch.int32 and col32.dtype == torch.int32 and tval.dtype == torch.float32
+        assert rowptr32.numel() == n + 1 and col32.numel() == tval.numel()
+        self.n, self.rowptr, self.col, self.tval, self.fill = n, rowptr32.contiguous(), col32.contiguous(), tval.contiguous(), float(fill)
+        self.r0, self.r1 = r0, n if r1 is None else r1
+
+    @classmethod
+    def from_graph(cls, graph, adj: torch.Tensor | None, factor: float, r0: int = 0, r1: int | None = None):
+        """Wish distances at the stored pairs: ``(1/a)^factor / max`` like ``cont2dist`` (utils.py:75-80).
+        With the dense f64 contact matrix ``adj`` the values are gathered from it (bit-identical to the dense
+        target at those pairs); without it they come from the graph's f32 edge values."""
+        r32, c32 = graph.i32()
+        row = graph.storage.row()
+        a = adj[row, graph.col].double() if adj is not None else graph.value.double()
+        dist = (1.0 / a) ** factor
+        tval = (dist / dist.max()).float()
+        return cls(graph.n, r32, c32, tval, 1.0, r0, r1)
+
+    def rows(self, r0: int, r1: int):
+        return SparseWishTarget(self.n, self.rowptr, self.col, self.tval, self.fill, r0, r1)
+
+    def t_moments(self) -> torch.Tensor:
+        if getattr(self, "_tmom", None) is None:
+            zeros = torch.zeros(self.n, 3, dtype=torch.float32, device=self.tval.device)
+            m, _ = pairloss_raw(zeros, self, N.PAIR_MOMENTS, 0.0, 0.0)
+            out = torch.zeros_like(m)
+            out[4:6] = m[4:6]
+            self._tmom = out
+        return self._tmom
+
+
 # ------------------------------------------------------------------------------ pair loss
 class _PairWorkspace:
     """Per (device, n, row block) scratch for the cross-CTA reductions, re-sized when the kernel
@@ -96,11 +134,11 @@ class _PairWorkspace:
     _cache: dict = {}
 
     @classmethod
-    def get(cls, device, n, r0, r1):
-        key = (device.index, n, r0, r1, N.tuning_epoch())
+    def get(cls, device, n, r0, r1, sparse: bool = False):
+        key = (device.index, n, r0, r1, N.tuning_epoch(), sparse)
         ws = cls._cache.get(key)
         if ws is None:
-            need = N.lib().hicgat_pairloss_workspace_bytes(n, r0, r1)
+            need = (N.lib().hicgat_pairloss_sparse_workspace_bytes if sparse else N.lib().hicgat_pairloss_workspace_bytes)(n, r0, r1)
             # zero-filled once and used for nothing else: calls pass HICGAT_PAIR_WS_CLEAN
             ws = torch.zeros(need, dtype=torch.uint8, device=device)
             cls._cache[key] = ws
@@ -108,7 +146,25 @@ class _PairWorkspace:
 
 
 def pairloss_raw(coords: torch.Tensor, target: WishTarget, mode: int, c_mse: float, c_l1: float, moments=None, grad=None):
-    """One launch of ``hicgat_pairloss_fwd_bwd``: returns ``(moments f64[8], grad f32[n,3])``."""
+    """One launch of ``hicgat_pairloss_fwd_bwd`` (dense f32 target) or ``hicgat_pairloss_sparse_fwd_bwd``
+    (implicit target): returns ``(moments f64[8], grad f32[n,3])``."""
+    if isinstance(target, SparseWishTarget):
+        _cuda(coords)
+        if coords.dtype != torch.float32 or coords.shape != (target.n, 3):
+            raise RuntimeError(f"coords must be float32 [n,3] with n={target.n}, got {coords.dtype} {tuple(coords.shape)}")
+        coords = coords.contiguous()
+        n = target.n
+        if moments is None:
+            moments = torch.empty(N.PAIR_NMOM, dtype=torch.float64, device=coords.device)
+        if grad is None and (mode & 3):
+            grad = torch.empty(n, 3, dtype=torch.float32, device=coords.device)
+        ws = _PairWorkspace.get(coords.device, n, target.r0, target.r1, sparse=True)
+        rc = N.lib().hicgat_pairloss_sparse_fwd_bwd(
+            coords.data_ptr(), target.rowptr.data_ptr(), target.col.data_ptr(), target.tval.data_ptr(), target.fill, n, target.r0, target.r1,
+            mode | N.PAIR_WS_CLEAN, c_mse, c_l1, moments.data_ptr(), _ptr(grad), ws.data_ptr(), ws.numel(), _stream(),
+        )
+        N.check(rc, "hicgat_pairloss_sparse_fwd_bwd")
+        return moments, grad
     _cuda(coords, target.data)
     if coords.dtype != torch.float32 or coords.shape != (target.n, 3):
         raise RuntimeError(f"coords must be float32 [n,3] with n={target.n}, got {coords.dtype} {tuple(coords.shape)}")

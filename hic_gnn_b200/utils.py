@@ -74,3 +74,10 @@ def wish_target(adj: torch.Tensor, factor: float) -> ops.WishTarget:
     """Same values as ``cont2dist(adj, factor).float()`` (the per-iteration cast at
     HiC-GNN_main.py:127) written once, directly in the layout the loss kernel streams."""
     return ops.cont2dist(adj.contiguous(), factor, want_f64=False, want_f32=True)[1]
+
+
+def sparse_wish_target(data: Data, factor: float) -> ops.SparseWishTarget:
+    """Implicit form of :func:`wish_target` for sparse maps (row f-4): wish distances only at the
+    stored pairs of ``data.edge_index``; every other pair is 1.0, the diagonal 0.  Same loss, no N x N
+    array."""
+    return ops.SparseWishTarget.from_graph(data.edge_index, data.y, factor)

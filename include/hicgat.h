@@ -103,6 +103,21 @@ HICGAT_API int hicgat_pairloss_fwd_bwd_packed(const float* coords, const float* 
 HICGAT_API int hicgat_pairloss_set_tuning(int rows_per_cta, int variant);
 
 /* ------------------------------------------------------------------------------------
+ * (next row f-4) The same loss against an IMPLICIT target for sparse maps: after cont2dist every
+ * zero-contact pair has wish distance `fill` (= 1.0: max/max, utils.py:78-80) and the diagonal 0, so
+ * only the nnz pairs that carry a contact need a stored value.  `rowptr` int32[n+1] / `col` int32[nnz]
+ * is the symmetric diagonal-free CSR pattern of load_input, `tval` f32[nnz] the wish distance of each
+ * stored pair.  Result contract identical to hicgat_pairloss_fwd_bwd (moments of rows [r0,r1), this
+ * rank's gradient contribution, sum over ranks when sharded); no N x N array exists anywhere:
+ * a compute-only pass over the constant background + a CSR correction pass.
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API size_t hicgat_pairloss_sparse_workspace_bytes(int64_t n, int64_t r0, int64_t r1);
+HICGAT_API int hicgat_pairloss_sparse_fwd_bwd(const float* coords, const int32_t* rowptr, const int32_t* col,
+                                   const float* tval, float fill, int64_t n, int64_t r0, int64_t r1,
+                                   uint32_t mode, float c_mse, float c_l1, double* moments, float* grad,
+                                   void* workspace, size_t workspace_bytes, hicgat_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * (3) Exchange step of the row-sharded loss: one-shot all-reduce of every rank's partial
  * [8 x f64 moments | 3n x f32 gradient] (64 + 12n bytes, what hicgat_pairloss_fwd_bwd writes when
  * given moments = base and grad = base + 64 bytes) over NVLink peer memory.  No counterpart in
