@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--emulate-world", type=int, default=0, help="profiling aid: on ONE GPU run rank 0's row block of a W-way split (not a bench line)")
     ap.add_argument("--no-measure-copy", dest="measure_copy", action="store_false", help="skip the same-process copy-bandwidth control")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the single-GPU training step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the implicit-target (row f-4) leg")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -315,6 +316,9 @@ def run_native(args):
     if want_train:
         rowptr, col, val = ops.csr_from_dense(adj)
         graph = CSRGraph(rowptr, col, val, n)
+    sparse_tgt = None
+    if graph is not None and not args.no_sparse:  # row f-4: the same target in implicit form (values gathered from adj: bit-identical)
+        sparse_tgt = ops.SparseWishTarget.from_graph(graph, adj, 1.0, r0, r1)
     want_cpu = (not args.no_cpu_baseline) and world == 1 and rank == 0
     sample_rows = max(8, min(n, int(args.cpu_sample_pairs // n)))
     cpu_truth = None
@@ -452,6 +456,56 @@ def run_native(args):
                                   "h2d_bytes_per_step": int(host_coords.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 8),
                                   "note": "same call with the f32 target resident in HBM (how the training loop uses it): per step coords H2D, moments+gradient D2H, host sync"}
 
+    # ---- (2c) row f-4: the same loss against the implicit (sparse) target -- no N x N array, compute-bound
+    sparse_out = None
+    if sparse_tgt is not None:
+        sp_fn = sharding.make_sharded_pair_loss(n, sharding.cuda_local_fn(sparse_tgt, mode, c_mse, c_l1), dev, transport=args.transport,
+                                                local_split_fn=sharding.cuda_local_split_fn(sparse_tgt, mode, c_mse, c_l1))
+        for _ in range(W):
+            sm_, sg_ = sp_fn(coords)
+        barrier()
+        start.record()
+        for _ in range(K):
+            sm_, sg_ = sp_fn(coords)
+        stop.record()
+        barrier()
+        s_ms = max_over_ranks(start.elapsed_time(stop))
+        k0, k1 = int(sparse_tgt.rowptr[r0]), int(sparse_tgt.rowptr[r1])
+        sparse_out = {"value": float(n) * float(n) * K / (s_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": s_ms / K, "nnz_this_rank": k1 - k0,
+                      "target_bytes_this_rank": (k1 - k0) * 8 + (n + 1) * 4, "bound": "fp32/mufu (no target stream)",
+                      "mse_matches_dense": abs(float(sm_[0]) - float(moments[0])) <= 1e-6 * abs(float(moments[0]))}
+        if not args.no_e2e:  # from host buffers: the CSR slice of this rank + coords go up every step, the result comes back
+            Ke = args.e2e_steps or min(K, 10)
+            h_col = torch.empty(k1 - k0, dtype=torch.int32, pin_memory=True); h_col.copy_(sparse_tgt.col[k0:k1])
+            h_val = torch.empty(k1 - k0, dtype=torch.float32, pin_memory=True); h_val.copy_(sparse_tgt.tval[k0:k1])
+            h_ptr = torch.empty(n + 1, dtype=torch.int32, pin_memory=True); h_ptr.copy_(sparse_tgt.rowptr)
+            h_xyz = torch.empty(n, 3, dtype=torch.float32, pin_memory=True); h_xyz.copy_(coords)
+            h_out = torch.empty(N.PAIR_NMOM + 3 * n, dtype=torch.float64, pin_memory=True)
+            d_xyz = torch.empty_like(coords)
+
+            def sparse_e2e_step():
+                sparse_tgt.col[k0:k1].copy_(h_col, non_blocking=True)
+                sparse_tgt.tval[k0:k1].copy_(h_val, non_blocking=True)
+                sparse_tgt.rowptr.copy_(h_ptr, non_blocking=True)
+                d_xyz.copy_(h_xyz, non_blocking=True)
+                m_, g_ = sp_fn(d_xyz)
+                h_out[: N.PAIR_NMOM].copy_(m_, non_blocking=True)
+                h_out[N.PAIR_NMOM:].copy_(g_.reshape(-1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            for _ in range(2):
+                sparse_e2e_step()
+            barrier()
+            start.record()
+            for _ in range(Ke):
+                sparse_e2e_step()
+            stop.record()
+            barrier()
+            se_ms = max_over_ranks(start.elapsed_time(stop))
+            sparse_out["e2e"] = {"value": float(n) * float(n) * Ke / (se_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": se_ms / Ke,
+                                 "h2d_bytes_per_step": int((k1 - k0) * 8 + (n + 1) * 4 + n * 12), "d2h_bytes_per_step": int(h_out.numel() * 8),
+                                 "note": "host CSR slice (col, wish value) + rowptr + coords up, moments + gradient down, every step"}
+
     # ---- (3) whole training step: GAT net forward, fused loss, backward, Adam
     train_out = None
     if want_train:
@@ -522,6 +576,7 @@ def run_native(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "train": train_out,
+            "sparse_target": sparse_out,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(windows),
             "check": {"mse": mse},

@@ -134,8 +134,17 @@ def make_sharded_pair_loss(n: int, local_fn, device, group=None, moment_const=No
 
 
 def cuda_local_fn(target, mode: int, c_mse: float, c_l1: float):
-    """The production ``local_fn``: hicgat_pairloss_fwd_bwd_packed on this rank's WishTarget."""
-    from .ops import _PairWorkspace, _cuda, _stream
+    """The production ``local_fn`` of the NCCL exchange: fills the packed f64 buffer for this rank's
+    target (dense: hicgat_pairloss_fwd_bwd_packed in one launch; implicit/sparse: the split call + a pack)."""
+    from .ops import SparseWishTarget, _PairWorkspace, _cuda, _stream, pairloss_raw
+
+    if isinstance(target, SparseWishTarget):
+        def sparse_fn(coords: torch.Tensor, packed: torch.Tensor):
+            m, g = pairloss_raw(coords, target, mode, c_mse, c_l1)
+            packed[: N.PAIR_NMOM].copy_(m)
+            packed[N.PAIR_NMOM:].copy_(g.reshape(-1))
+
+        return sparse_fn
 
     def fn(coords: torch.Tensor, packed: torch.Tensor):
         _cuda(coords, packed)
@@ -150,17 +159,11 @@ def cuda_local_fn(target, mode: int, c_mse: float, c_l1: float):
 
 
 def cuda_local_split_fn(target, mode: int, c_mse: float, c_l1: float):
-    """``local_fn`` of :class:`P2PShardedPairLoss`: hicgat_pairloss_fwd_bwd writing moments / grad
-    straight into the symmetric partial."""
-    from .ops import _PairWorkspace, _cuda, _stream
+    """``local_fn`` of :class:`P2PShardedPairLoss`: the loss kernel writes moments / grad straight into
+    the symmetric partial (dense or implicit target)."""
+    from .ops import pairloss_raw
 
     def fn(coords: torch.Tensor, moments: torch.Tensor, grad: torch.Tensor):
-        _cuda(coords, moments, grad)
-        ws = _PairWorkspace.get(coords.device, target.n, target.r0, target.r1)
-        rc = N.lib().hicgat_pairloss_fwd_bwd(
-            coords.contiguous().data_ptr(), target.data.data_ptr(), target.pitch, target.n, target.r0, target.r1,
-            mode | N.PAIR_WS_CLEAN, c_mse, c_l1, moments.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(), _stream(),
-        )
-        N.check(rc, "hicgat_pairloss_fwd_bwd")
+        pairloss_raw(coords, target, mode, c_mse, c_l1, moments=moments, grad=grad)
 
     return fn
