@@ -381,22 +381,30 @@ def run_native(args):
 
     for _ in range(W):
         loss_step()
-    barrier()
-    launches0 = N.launch_count()
-    w0 = time.time()
-    profile_region("loss", True)
-    torch.cuda.nvtx.range_push("hicgat_loss")
-    start.record()
-    for k in range(K):
-        moments, grad = loss_step(k)
-    stop.record()
-    barrier()
-    torch.cuda.nvtx.range_pop()
-    profile_region("loss", False)
-    w1 = time.time()
-    launches = N.launch_count() - launches0
-    elapsed_ms = max_over_ranks(start.elapsed_time(stop))
-    kern_ms = sum(a.elapsed_time(b) for a, b in ev) / K
+    attempts = 0
+    while True:
+        attempts += 1
+        barrier()
+        launches0 = N.launch_count()
+        w0 = time.time()
+        profile_region("loss", True)
+        torch.cuda.nvtx.range_push("hicgat_loss")
+        start.record()
+        for k in range(K):
+            moments, grad = loss_step(k)
+        stop.record()
+        barrier()
+        torch.cuda.nvtx.range_pop()
+        profile_region("loss", False)
+        w1 = time.time()
+        launches = N.launch_count() - launches0
+        elapsed_ms = max_over_ranks(start.elapsed_time(stop))
+        kern_ms = sum(a.elapsed_time(b) for a, b in ev) / K
+        # A host-side stall (noisy neighbour, GC) leaves the GPU queue empty and shows up as step time far above
+        # the kernel time; like a throttled run it is re-measured ONCE and the fact is reported.
+        stalled = max_over_ranks(1.0 if elapsed_ms / K > 1.25 * kern_ms + 0.1 else 0.0) > 0
+        if not stalled or attempts == 2:
+            break
     value = float(n) * float(n) * K / (elapsed_ms * 1e-3) / 1e9
     mse = float(moments[0]) / (float(n) * float(n))
     windows = {"loss": (w0, w1)}
@@ -567,7 +575,7 @@ def run_native(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "n_loci": n, "density": density, "pairs_per_step": float(n) * float(n), "loss_mode": args.loss_mode,
                        "parallelism": f"rows{world}" if world > 1 else ("single" if not args.emulate_world else f"rank0-of-{args.emulate_world} (emulated, NOT a bench line)"), "rows_per_rank": nloc, "exchange": transport,
-                       "l2": f"no flush: each step streams {target_bytes / 1e6:.0f} MB of target per rank (L2 is 126 MB)",
+                       "timed_attempts": attempts, "l2": f"no flush: each step streams {target_bytes / 1e6:.0f} MB of target per rank (L2 is 126 MB)",
                        "setup_s": round(t_setup, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "pairloss_tma_kernel" if args.variant == 0 else "pairloss_ldg_kernel", "kernel_ms": kern_ms, "algorithmic_bytes": nloc * n * 4.0, "peak_source": peak_src,

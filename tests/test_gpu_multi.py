@@ -44,6 +44,20 @@ def _worker(rank, world, port, n, tmpdir):
             gathered = [torch.empty_like(g_s) for _ in range(world)]
             dist.all_gather(gathered, g_s.contiguous())
             assert all(torch.equal(gathered[0], t) for t in gathered)
+        # implicit (sparse) target, row-sharded over the same two transports
+        from hic_gnn_b200 import utils
+
+        data = utils.load_input(adj.cpu().numpy().copy(), torch.zeros(n, 4).numpy(), device=f"cuda:{rank}")
+        sp_full = utils.sparse_wish_target(data, 1.0)
+        sp_loc = sp_full.rows(r0, r1)
+        for transport in ("nccl", "p2p"):
+            red = ops.sharded_reducer(sp_loc, "mse_moments", transport=transport)
+            loss_s, mom_s = hg.pairwise_loss(coords, sp_loc, "mse_moments", reducer=red)
+            (g_s,) = torch.autograd.grad(loss_s, coords)
+            loss_1, mom_1 = hg.pairwise_loss(coords, full, "mse_moments")
+            (g_1,) = torch.autograd.grad(loss_1, coords)
+            assert abs(float(loss_s) - float(loss_1)) <= 1e-6 * abs(float(loss_1)), (transport, float(loss_s), float(loss_1))
+            assert rel_err(mom_s, mom_1) < 1e-6 and rel_err(g_s, g_1) < 1e-5
         open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
