@@ -246,7 +246,8 @@ def sharded_reducer(target: WishTarget, mode: str, group=None, transport: str = 
     const = None
     if m & N.PAIR_MOMENTS_D and not m & N.PAIR_MOMENTS:
         const = sharding.allreduce_packed(target.t_moments().clone(), group)  # global sum t, sum t^2: once
-    return sharding.make_sharded_pair_loss(n, fn, target.data.device, group, moment_const=const, transport=transport, local_split_fn=split_fn)
+    device = target.tval.device if isinstance(target, SparseWishTarget) else target.data.device
+    return sharding.make_sharded_pair_loss(n, fn, device, group, moment_const=const, transport=transport, local_split_fn=split_fn)
 
 
 def pair_moments(coords: torch.Tensor, target: WishTarget) -> torch.Tensor:
