@@ -162,7 +162,10 @@ __device__ __forceinline__ void store_rows_tile(float (*__restrict__ bs)[BN], co
 template <bool TRANSPOSED, int BM_>
 __global__ void __launch_bounds__(kThreads) gat_dense_spmm_kernel(const DenseArgs A, const float* __restrict__ X, const float* __restrict__ v0,
                                                                   const float* __restrict__ v1, const float* __restrict__ s0,
-                                                                  const float* __restrict__ s1, float* __restrict__ out) {
+                                                                  const float* __restrict__ s1, float* __restrict__ out, float* __restrict__ part,
+                                                                  int kper) {
+    // gridDim.z > 1: split-K over the sources/targets; CTA z accumulates k in [z*kper, (z+1)*kper) and writes its
+    // raw tile to part[z]; gat_dense_combine_kernel adds the splits in order and applies the epilogue
     constexpr int TM_ = BM_ / 8;
     __shared__ __align__(16) Tiles<BM_> T;
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -177,21 +180,37 @@ __global__ void __launch_bounds__(kThreads) gat_dense_spmm_kernel(const DenseArg
         for (int c = 0; c < TN; ++c) acc[r][c] = 0.f;
 
     float4 breg[4];
-    const int ksteps = (A.n + BK - 1) / BK;
-    gen_att_tile<TRANSPOSED, BM_>(T.a[0], A, h, m0, 0, t);
-    load_rows_tile(breg, X, F, A.n, 0, c0, t);
+    const int kbeg = blockIdx.z * kper, kend = min(A.n, kbeg + kper);  // kper is a multiple of BK
+    const int ksteps = (kend - kbeg + BK - 1) / BK;
+    gen_att_tile<TRANSPOSED, BM_>(T.a[0], A, h, m0, kbeg, t);
+    load_rows_tile(breg, X, F, A.n, kbeg, c0, t);
     store_rows_tile(T.b[0], breg, t);
     __syncthreads();
     for (int ks = 0; ks < ksteps; ++ks) {
         const int cur = ks & 1, nxt = cur ^ 1;
         const bool more = ks + 1 < ksteps;
-        if (more) load_rows_tile(breg, X, F, A.n, (ks + 1) * BK, c0, t);   // in flight during the FMAs
+        if (more) load_rows_tile(breg, X, F, A.n, kbeg + (ks + 1) * BK, c0, t);   // in flight during the FMAs
         mma_step<BM_>(acc, T.a[cur], T.b[cur], ty, tx);
         if (more) {
-            gen_att_tile<TRANSPOSED, BM_>(T.a[nxt], A, h, m0, (ks + 1) * BK, t);
+            gen_att_tile<TRANSPOSED, BM_>(T.a[nxt], A, h, m0, kbeg + (ks + 1) * BK, t);
             store_rows_tile(T.b[nxt], breg, t);
         }
         __syncthreads();
+    }
+    if (gridDim.z > 1) {  // raw partial tile; epilogue in the combine kernel
+        float* dst = part + (size_t)blockIdx.z * A.n * F;
+#pragma unroll
+        for (int r = 0; r < TM_; ++r) {
+            const int gm = m0 + (TM_ == 8 ? out_row(ty, r) : ty * 4 + r);
+            if (gm >= A.n) continue;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int gc = c0 + half * 64 + tx * 4;
+                *reinterpret_cast<float4*>(dst + (size_t)gm * F + gc) =
+                    make_float4(acc[r][half * 4 + 0], acc[r][half * 4 + 1], acc[r][half * 4 + 2], acc[r][half * 4 + 3]);
+            }
+        }
+        return;
     }
 #pragma unroll
     for (int r = 0; r < TM_; ++r) {
@@ -211,6 +230,31 @@ __global__ void __launch_bounds__(kThreads) gat_dense_spmm_kernel(const DenseArg
             }
             *reinterpret_cast<float4*>(out + (size_t)gm * F + gc) = o;
         }
+    }
+}
+
+// out[m, c] = sum_z part[z][m, c] (+ bias[c])  or  (+ s0[m,h] v0[c] + s1[m,h] v1[c]) -- split order fixed
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256) gat_dense_combine_kernel(const float* __restrict__ part, int nsplit, int n, int H, int C,
+                                                                const float* __restrict__ v0, const float* __restrict__ v1,
+                                                                const float* __restrict__ s0, const float* __restrict__ s1, float* __restrict__ out) {
+    const int F = H * C;
+    const size_t total4 = (size_t)n * F / 4;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (size_t)gridDim.x * blockDim.x) {
+        float4 o = __ldcg(reinterpret_cast<const float4*>(part) + q);
+        for (int z = 1; z < nsplit; ++z) {
+            const float4 p = __ldcg(reinterpret_cast<const float4*>(part + (size_t)z * n * F) + q);
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        const int m = (int)(q * 4 / F), c = (int)(q * 4 % F), h = c / C;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(v0 + c));
+        if (!TRANSPOSED) { o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        else {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(v1 + c));
+            const float e0 = s0[m * H + h], e1 = s1[m * H + h];
+            o.x += e0 * a.x + e1 * b.x; o.y += e0 * a.y + e1 * b.y; o.z += e0 * a.z + e1 * b.z; o.w += e0 * a.w + e1 * b.w;
+        }
+        reinterpret_cast<float4*>(out)[q] = o;
     }
 }
 
@@ -362,11 +406,12 @@ __global__ void gat_dense_reduce_partials_kernel(const float* __restrict__ rowpa
 using namespace hicgat;
 
 namespace {
+constexpr int kMaxSplit = 4;
 struct DenseLayout {
-    int words, ntm, ntn;
-    size_t off_rmax, off_rinv, off_rowdot, off_dsrc, off_ddst, off_rowpart, off_colpart, total;
+    int words, ntm, ntn, nsplit, kper;
+    size_t off_rmax, off_rinv, off_rowdot, off_dsrc, off_ddst, off_rowpart, off_colpart, off_split, total;
 };
-DenseLayout dense_layout(int64_t n, int H) {
+DenseLayout dense_layout(int64_t n, int H, int C = 0) {
     DenseLayout L;
     L.words = (int)((n + 31) / 32);
     L.ntm = (int)((n + BM - 1) / BM);
@@ -379,7 +424,17 @@ DenseLayout dense_layout(int64_t n, int H) {
     L.off_ddst = L.off_dsrc + nh;
     L.off_rowpart = L.off_ddst + nh;
     L.off_colpart = L.off_rowpart + align_up(sizeof(float) * (size_t)L.ntn * n * H, 256);
-    L.total = L.off_colpart + align_up(sizeof(float) * (size_t)L.ntm * n * H, 256);
+    L.off_split = L.off_colpart + align_up(sizeof(float) * (size_t)L.ntm * n * H, 256);
+    // split-K of the two SpMM-shaped GEMMs: 64-row tiles are the efficient ones (8x8 per thread), so small
+    // maps get their parallelism from splitting the k range instead of from smaller tiles
+    L.nsplit = 1;
+    L.kper = (int)((n + BK - 1) / BK * BK);
+    if (C > 0) {
+        const int64_t ctas = (int64_t)L.ntm * H * (C / BN);
+        while (L.nsplit < kMaxSplit && ctas * L.nsplit < 2 * 148 && n / (L.nsplit * 2) >= 8 * BK) L.nsplit *= 2;
+        L.kper = (int)(((n + L.nsplit - 1) / L.nsplit + BK - 1) / BK * BK);
+    }
+    L.total = L.off_split + (L.nsplit > 1 ? sizeof(float) * (size_t)L.nsplit * n * H * C : 0);
     return L;
 }
 bool dense_supported(int H, int C) { return (H == 1 || H == 2 || H == 4) && C % BN == 0 && C >= BN; }
@@ -399,7 +454,7 @@ extern "C" int hicgat_gat_dense_build_mask(const int32_t* rowptr, const int32_t*
 
 extern "C" size_t hicgat_gat_dense_workspace_bytes(int64_t n, int heads, int channels) {
     if (n <= 0 || !dense_supported(heads, channels)) return 0;
-    return dense_layout(n, heads).total;
+    return dense_layout(n, heads, channels).total;
 }
 
 // forward: a_src/a_dst (logit halves) from the caller (gat logit kernel), row stats into the workspace
@@ -410,7 +465,7 @@ extern "C" int hicgat_gat_dense_fwd(const int32_t* rowptr, const int32_t* col, c
     HICGAT_REQUIRE(rowptr && col && mask && xl && a_src && a_dst && bias && out && workspace, "hicgat_gat_dense_fwd: null pointer");
     HICGAT_REQUIRE(n > 0 && n < (1ll << 24) && dense_supported(heads, channels), "hicgat_gat_dense_fwd: unsupported n/heads/channels (%lld,%d,%d)", (long long)n, heads, channels);
     HICGAT_REQUIRE(aligned16(xl) && aligned16(out) && aligned16(bias), "hicgat_gat_dense_fwd: 16-byte alignment required");
-    const DenseLayout L = dense_layout(n, heads);
+    const DenseLayout L = dense_layout(n, heads, channels);
     if (workspace_bytes < L.total) { set_error("hicgat_gat_dense_fwd: workspace %zu < required %zu", workspace_bytes, L.total); return HICGAT_ERR_WORKSPACE; }
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     float* rmax = reinterpret_cast<float*>(ws + L.off_rmax);
@@ -424,12 +479,13 @@ extern "C" int hicgat_gat_dense_fwd(const int32_t* rowptr, const int32_t* col, c
     HICGAT_CHECK_LAUNCH("gat_row_stats_kernel");
     DenseArgs A{(int)n, heads, channels, L.words, mask, a_src, a_dst, rmax, rinv, slope};
     const unsigned ytiles = (unsigned)(heads * (channels / BN));
-    if ((int64_t)L.ntm * ytiles >= 4 * 148) {  // enough 64-row tiles to fill the machine
-        gat_dense_spmm_kernel<false, 64><<<dim3((unsigned)L.ntm, ytiles), kThreads, 0, stream>>>(A, xl, bias, nullptr, nullptr, nullptr, out);
-    } else {                                   // small maps: 32-row tiles double the CTA count
-        gat_dense_spmm_kernel<false, 32><<<dim3((unsigned)((n + 31) / 32), ytiles), kThreads, 0, stream>>>(A, xl, bias, nullptr, nullptr, nullptr, out);
-    }
+    float* split = reinterpret_cast<float*>(ws + L.off_split);
+    gat_dense_spmm_kernel<false, 64><<<dim3((unsigned)L.ntm, ytiles, (unsigned)L.nsplit), kThreads, 0, stream>>>(A, xl, bias, nullptr, nullptr, nullptr, out, split, L.kper);
     HICGAT_CHECK_LAUNCH("gat_dense_spmm_kernel<fwd>");
+    if (L.nsplit > 1) {
+        gat_dense_combine_kernel<false><<<148 * 4, 256, 0, stream>>>(split, L.nsplit, (int)n, heads, channels, bias, nullptr, nullptr, nullptr, out);
+        HICGAT_CHECK_LAUNCH("gat_dense_combine_kernel<fwd>");
+    }
     return HICGAT_OK;
 }
 
@@ -443,7 +499,7 @@ extern "C" int hicgat_gat_dense_bwd(const uint32_t* mask, int64_t n, int heads, 
     HICGAT_REQUIRE(mask && xl && a_src && a_dst && att_l && att_r && bias && out && gout && dxl && d_a_src && d_a_dst && workspace, "hicgat_gat_dense_bwd: null pointer");
     HICGAT_REQUIRE(n > 0 && n < (1ll << 24) && dense_supported(heads, channels), "hicgat_gat_dense_bwd: unsupported n/heads/channels");
     HICGAT_REQUIRE(aligned16(xl) && aligned16(out) && aligned16(gout) && aligned16(dxl) && aligned16(att_l) && aligned16(att_r) && aligned16(bias), "hicgat_gat_dense_bwd: 16-byte alignment required");
-    const DenseLayout L = dense_layout(n, heads);
+    const DenseLayout L = dense_layout(n, heads, channels);
     if (workspace_bytes < L.total) { set_error("hicgat_gat_dense_bwd: workspace %zu < required %zu", workspace_bytes, L.total); return HICGAT_ERR_WORKSPACE; }
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     float* rmax = reinterpret_cast<float*>(ws + L.off_rmax);
@@ -466,11 +522,12 @@ extern "C" int hicgat_gat_dense_bwd(const uint32_t* mask, int64_t n, int heads, 
     gat_dense_reduce_partials_kernel<<<(nH + 255) / 256, 256, 0, stream>>>(rowpart, colpart, nH, L.ntn, L.ntm, d_a_dst, d_a_src);
     HICGAT_CHECK_LAUNCH("gat_dense_reduce_partials_kernel");
     const unsigned ytiles = (unsigned)(heads * (channels / BN));
-    if ((int64_t)L.ntm * ytiles >= 4 * 148) {
-        gat_dense_spmm_kernel<true, 64><<<dim3((unsigned)L.ntm, ytiles), kThreads, 0, stream>>>(A, gout, att_l, att_r, d_a_src, d_a_dst, dxl);
-    } else {
-        gat_dense_spmm_kernel<true, 32><<<dim3((unsigned)((n + 31) / 32), ytiles), kThreads, 0, stream>>>(A, gout, att_l, att_r, d_a_src, d_a_dst, dxl);
-    }
+    float* split = reinterpret_cast<float*>(ws + L.off_split);
+    gat_dense_spmm_kernel<true, 64><<<dim3((unsigned)L.ntm, ytiles, (unsigned)L.nsplit), kThreads, 0, stream>>>(A, gout, att_l, att_r, d_a_src, d_a_dst, dxl, split, L.kper);
     HICGAT_CHECK_LAUNCH("gat_dense_spmm_kernel<bwd>");
+    if (L.nsplit > 1) {
+        gat_dense_combine_kernel<true><<<148 * 4, 256, 0, stream>>>(split, L.nsplit, (int)n, heads, channels, att_l, att_r, d_a_src, d_a_dst, dxl);
+        HICGAT_CHECK_LAUNCH("gat_dense_combine_kernel<bwd>");
+    }
     return HICGAT_OK;
 }
