@@ -65,6 +65,8 @@ def parse_args():
     ap.add_argument("--no-measure-copy", dest="measure_copy", action="store_false", help="skip the same-process copy-bandwidth control")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the single-GPU training step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-sparse", action="store_true", help="skip the implicit-target (row f-4) leg")
+    ap.add_argument("--model", default="gat", choices=["gat", "net", "gat_v2"], help="network of the training-step leg: the GAT net (GATNetSelectiveResidualsUpdated), "
+                    "models.Net (SAGEConv, HiC-GNN) or GATNetHeadsChanged3LayersLeakyReLUv2")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -519,7 +521,8 @@ def run_native(args):
     if want_train:
         Kt = args.train_steps or min(K, 10)
         torch.manual_seed(42)
-        model = models.GATNetSelectiveResidualsUpdated().to(dev)
+        model_cls = {"gat": models.GATNetSelectiveResidualsUpdated, "net": models.Net, "gat_v2": models.GATNetHeadsChanged3LayersLeakyReLUv2}[args.model]
+        model = model_cls().to(dev)
         x = synth.synthetic_features(n, device=dev)
         reducer = ops.sharded_reducer(target, "mse_moments", transport=args.transport) if world > 1 else None
         graphed = world == 1 and not args.no_cuda_graph  # the sharded step holds a per-step epoch argument: eager
@@ -542,7 +545,7 @@ def run_native(args):
         profile_region("train", False)
         windows["train"] = (w0, time.time())
         t_ms = max_over_ranks(start.elapsed_time(stop))
-        train_out = {"steps_per_s": Kt / (t_ms * 1e-3), "ms_per_step": t_ms / Kt, "steps": Kt, "model": "GATNetSelectiveResidualsUpdated",
+        train_out = {"steps_per_s": Kt / (t_ms * 1e-3), "ms_per_step": t_ms / Kt, "steps": Kt, "model": model_cls.__name__,
                      "loss": "mse + alpha*(1-pearson)", "nnz": graph.nnz, "total_loss": float(total),
                      "hicgat_launches_per_step": graph_kernels if graphed else (N.launch_count() - l0) / Kt, "gnn": "replicated", "loss_rows": "sharded" if world > 1 else "all", "cuda_graph": graphed}
         del tstep, model, x
