@@ -26,16 +26,45 @@ __device__ __forceinline__ double inv_pow(double a, double factor, int fkind) {
 }
 int factor_kind(double f) { return f == 1.0 ? 1 : f == 0.5 ? 2 : f == 2.0 ? 3 : 0; }
 
+// Both passes are pure streams with a long f64 division chain per element: what limits them is the
+// number of bytes a thread keeps in flight, so each thread owns TWO adjacent columns (one 16-byte load)
+// and walks TWO rows per iteration (4 independent divisions, 32 B outstanding per thread, 64 KB per SM).
+__device__ __forceinline__ void max_update(double& m, double a, double factor, int fkind, bool skip) {
+    const double v = inv_pow(a, factor, fkind);
+    // torch.max(nan_to_num(dist, posinf=0)): NaN -> 0, +inf -> 0 (utils.py:78)
+    if (!skip && v > m && v < CUDART_INF) m = v;
+}
+
 __global__ void __launch_bounds__(256) cont2dist_max_kernel(const double* __restrict__ adj, int64_t ld, int n, int r0, int r1,
                                                             double factor, int fkind, unsigned long long* max_bits) {
     double m = 0.0;
-    for (int i = r0 + blockIdx.x; i < r1; i += gridDim.x) {
-        const double* row = adj + (size_t)(i - r0) * ld;
-        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            if (j == i) continue;
-            const double v = inv_pow(row[j], factor, fkind);
-            // torch.max(nan_to_num(dist, posinf=0)): NaN -> 0, +inf -> 0 (utils.py:78)
-            if (v > m && v < CUDART_INF) m = v;
+    const bool vec = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(adj) & 15) == 0);
+    for (int i = r0 + 2 * blockIdx.x; i < r1; i += 2 * gridDim.x) {
+        const double* row0 = adj + (size_t)(i - r0) * ld;
+        const bool two = i + 1 < r1;
+        const double* row1 = two ? row0 + ld : row0;
+        if (vec) {
+            for (int j = 2 * threadIdx.x; j < n; j += 2 * blockDim.x) {
+                double2 a0, a1;
+                if (j + 1 < n) {
+                    a0 = __ldg(reinterpret_cast<const double2*>(row0 + j));
+                    a1 = __ldg(reinterpret_cast<const double2*>(row1 + j));
+                } else {
+                    a0 = make_double2(row0[j], 0.0);
+                    a1 = make_double2(row1[j], 0.0);
+                }
+                max_update(m, a0.x, factor, fkind, j == i);
+                max_update(m, a1.x, factor, fkind, !two || j == i + 1);
+                if (j + 1 < n) {
+                    max_update(m, a0.y, factor, fkind, j + 1 == i);
+                    max_update(m, a1.y, factor, fkind, !two || j + 1 == i + 1);
+                }
+            }
+        } else {
+            for (int j = threadIdx.x; j < n; j += blockDim.x) {
+                max_update(m, row0[j], factor, fkind, j == i);
+                max_update(m, row1[j], factor, fkind, !two || j == i + 1);
+            }
         }
     }
     __shared__ double s[8];
@@ -50,23 +79,53 @@ __global__ void __launch_bounds__(256) cont2dist_max_kernel(const double* __rest
     }
 }
 
+__device__ __forceinline__ double wish_value(double a, bool diag, double factor, int fkind, double mx) {
+    double v = diag ? 0.0 : inv_pow(a, factor, fkind);   // utils.py:76-77
+    if (v != v) v = 0.0;                                  // nan_to_num: NaN -> 0
+    else if (v == CUDART_INF) v = mx;                     // posinf -> max (utils.py:79)
+    else if (v == -CUDART_INF) v = -1.7976931348623157e308;
+    return v / mx;                                        // utils.py:80
+}
+
+// thread = two adjacent columns, rows strided by gridDim.y, two rows per iteration
 __global__ void __launch_bounds__(256) cont2dist_apply_kernel(const double* __restrict__ adj, int64_t ld, int n, int r0, int r1,
                                                               double factor, int fkind, const double* __restrict__ max_in,
                                                               double* __restrict__ o64, int64_t ld64, float* __restrict__ o32, int64_t p32) {
     const double mx = *max_in;
-    for (int i = r0 + blockIdx.y; i < r1; i += gridDim.y) {
-        const double* row = adj + (size_t)(i - r0) * ld;
-        const int j = blockIdx.x * blockDim.x + threadIdx.x;
-        if (j < n) {
-            double v = (j == i) ? 0.0 : inv_pow(row[j], factor, fkind);  // utils.py:76-77
-            if (v != v) v = 0.0;                                          // nan_to_num: NaN -> 0
-            else if (v == CUDART_INF) v = mx;                             // posinf -> max (utils.py:79)
-            else if (v == -CUDART_INF) v = -1.7976931348623157e308;
-            v = v / mx;                                                   // utils.py:80
-            if (o64) o64[(size_t)(i - r0) * ld64 + j] = v;
-            if (o32) o32[(size_t)(i - r0) * p32 + j] = (float)v;
-        } else if (o32 && j < p32) {
-            o32[(size_t)(i - r0) * p32 + j] = 0.f;  // keep the 16-byte pitch padding defined
+    const int j = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const bool vin = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(adj) & 15) == 0);
+    const bool v64 = o64 && ((ld64 & 1) == 0) && ((reinterpret_cast<uintptr_t>(o64) & 15) == 0);
+    const bool v32 = o32 && ((p32 & 1) == 0) && ((reinterpret_cast<uintptr_t>(o32) & 7) == 0);
+    for (int i = r0 + 2 * blockIdx.y; i < r1; i += 2 * gridDim.y) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = i + u;
+            if (r >= r1) break;
+            const double* row = adj + (size_t)(r - r0) * ld;
+            if (j + 1 < n) {
+                const double2 a = vin ? __ldg(reinterpret_cast<const double2*>(row + j)) : make_double2(row[j], row[j + 1]);
+                const double w0 = wish_value(a.x, j == r, factor, fkind, mx), w1 = wish_value(a.y, j + 1 == r, factor, fkind, mx);
+                if (o64) {
+                    double* d = o64 + (size_t)(r - r0) * ld64 + j;
+                    if (v64) *reinterpret_cast<double2*>(d) = make_double2(w0, w1);
+                    else { d[0] = w0; d[1] = w1; }
+                }
+                if (o32) {
+                    float* d = o32 + (size_t)(r - r0) * p32 + j;
+                    if (v32) *reinterpret_cast<float2*>(d) = make_float2((float)w0, (float)w1);
+                    else { d[0] = (float)w0; d[1] = (float)w1; }
+                }
+            } else {
+                if (j < n) {
+                    const double w0 = wish_value(row[j], j == r, factor, fkind, mx);
+                    if (o64) o64[(size_t)(r - r0) * ld64 + j] = w0;
+                    if (o32) o32[(size_t)(r - r0) * p32 + j] = (float)w0;
+                }
+                // keep the 16-byte pitch padding defined
+                if (o32) {
+                    for (int c = max(j, n); c < min((int64_t)j + 2, p32); ++c) o32[(size_t)(r - r0) * p32 + c] = 0.f;
+                }
+            }
         }
     }
 }
@@ -235,7 +294,8 @@ extern "C" int hicgat_cont2dist_max_f64(const double* adj, int64_t ld, int64_t n
     HICGAT_REQUIRE(n > 0 && n < (1ll << 30) && r0 >= 0 && r1 >= r0 && r1 <= n && ld >= n, "hicgat_cont2dist_max_f64: bad shape");
     HICGAT_CUDA(cudaMemsetAsync(max_out, 0, sizeof(double), stream));
     if (r1 == r0) return HICGAT_OK;
-    const int grid = (int)((r1 - r0) < 148 * 8 ? (r1 - r0) : 148 * 8);
+    const int64_t row_pairs = (r1 - r0 + 1) / 2;
+    const int grid = (int)(row_pairs < 148 * 8 ? row_pairs : 148 * 8);
     cont2dist_max_kernel<<<grid, 256, 0, stream>>>(adj, ld, (int)n, (int)r0, (int)r1, factor, factor_kind(factor),
                                                    reinterpret_cast<unsigned long long*>(max_out));
     HICGAT_CHECK_LAUNCH("cont2dist_max_kernel");
@@ -252,7 +312,14 @@ extern "C" int hicgat_cont2dist_apply_f64(const double* adj, int64_t ld, int64_t
     HICGAT_REQUIRE(!out_f32 || pitch_f32 >= n, "hicgat_cont2dist_apply_f64: pitch_f32 < n");
     if (r1 == r0) return HICGAT_OK;
     const int64_t width = out_f32 ? pitch_f32 : n;
-    dim3 grid((unsigned)((width + 255) / 256), (unsigned)((r1 - r0) < 32768 ? (r1 - r0) : 32768));
+    // ~16 CTAs per SM in total; a thread owns two columns and walks row pairs with a stride of gridDim.y
+    // (a CTA per (column block, row) would be 6.4 M one-element CTAs at 50k loci)
+    const int64_t xblocks = (width + 511) / 512;
+    const int64_t row_pairs = (r1 - r0 + 1) / 2;
+    int64_t yblocks = (148 * 16 + xblocks - 1) / xblocks;
+    if (yblocks > row_pairs) yblocks = row_pairs;
+    if (yblocks < 1) yblocks = 1;
+    dim3 grid((unsigned)xblocks, (unsigned)yblocks);
     cont2dist_apply_kernel<<<grid, 256, 0, stream>>>(adj, ld, (int)n, (int)r0, (int)r1, factor, factor_kind(factor), max_in,
                                                      out_f64, ld_f64, out_f32, pitch_f32);
     HICGAT_CHECK_LAUNCH("cont2dist_apply_kernel");

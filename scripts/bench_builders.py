@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Timings of the one-off builders on one B200 at the benchmark sizes:
+wish-distance matrix (cont2dist, f64 -> padded f32) and CSR graph build (count, scan, fill, self loops,
+transposed permutation), against their algorithmic bytes.  One JSON object on stdout."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+
+from hic_gnn_b200 import ops, synth
+from hic_gnn_b200.graph import CSRGraph
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def main():
+    res = {}
+    for name, n, dens in (("c3", 2493, 0.95), ("c4", 9970, 0.07), ("c5", 49850, 0.01)):
+        adj = synth.synthetic_map_chunked(n, dens, device="cuda")
+        ms, (_, tgt) = timed(lambda: ops.cont2dist(adj, 1.0, want_f64=False, want_f32=True))
+        alg = n * n * (8 * 2 + 4)  # two f64 passes over the contacts + the f32 target written
+        res[f"cont2dist_f32_{name}"] = {"ms": ms, "algorithmic_GB": alg / 1e9, "GBps": alg / ms / 1e6}
+        del tgt
+        ms, (rowptr, col, val) = timed(lambda: ops.csr_from_dense(adj))
+        nnz = int(col.numel())
+        alg = n * n * 8 * 2 * 2 + nnz * 12  # count + fill each read A[i,:] and A[:,i]; col i64 + val f32 written
+        res[f"csr_from_dense_{name}"] = {"ms": ms, "nnz": nnz, "algorithmic_GB": alg / 1e9, "GBps": alg / ms / 1e6}
+        g = CSRGraph(rowptr, col, val, n)
+        ms, _ = timed(lambda: (g._cache.clear(), g.with_self_loops())[1], reps=2)
+        res[f"self_loops_and_perm_{name}"] = {"ms": ms}
+        ms, _ = timed(lambda: (g._cache.pop("sage", None), g.sage_weights())[1], reps=2)
+        res[f"sage_weights_{name}"] = {"ms": ms}
+        del adj, g, rowptr, col, val
+        torch.cuda.empty_cache()
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
