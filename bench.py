@@ -377,9 +377,14 @@ def run_native(args):
                                               local_split_fn=timed(sharding.cuda_local_split_fn(target, mode, c_mse, c_l1)))
     transport = "none" if world == 1 else ("p2p_oneshot" if isinstance(loss_fn, sharding.P2PShardedPairLoss) else "nccl_allreduce")
 
+    ev_end = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+
     def loss_step(k=None):
         cursor["k"] = k
-        return loss_fn(coords)
+        out = loss_fn(coords)
+        if k is not None:
+            ev_end[k].record()  # kernel end -> here = the exchange (barrier wait on the slowest rank + reduction) / the unpack
+        return out
 
     for _ in range(W):
         loss_step()
@@ -402,6 +407,7 @@ def run_native(args):
         launches = N.launch_count() - launches0
         elapsed_ms = max_over_ranks(start.elapsed_time(stop))
         kern_ms = sum(a.elapsed_time(b) for a, b in ev) / K
+        exch_ms = sum(ev[k][1].elapsed_time(ev_end[k]) for k in range(K)) / K
         # A host-side stall (noisy neighbour, GC) leaves the GPU queue empty and shows up as step time far above
         # the kernel time; like a throttled run it is re-measured ONCE and the fact is reported.
         stalled = max_over_ranks(1.0 if elapsed_ms / K > 1.25 * kern_ms + 0.1 else 0.0) > 0
@@ -577,7 +583,7 @@ def run_native(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "n_loci": n, "density": density, "pairs_per_step": float(n) * float(n), "loss_mode": args.loss_mode,
-                       "parallelism": f"rows{world}" if world > 1 else ("single" if not args.emulate_world else f"rank0-of-{args.emulate_world} (emulated, NOT a bench line)"), "rows_per_rank": nloc, "exchange": transport,
+                       "parallelism": f"rows{world}" if world > 1 else ("single" if not args.emulate_world else f"rank0-of-{args.emulate_world} (emulated, NOT a bench line)"), "rows_per_rank": nloc, "exchange": transport, "exchange_ms": exch_ms,
                        "timed_attempts": attempts, "l2": f"no flush: each step streams {target_bytes / 1e6:.0f} MB of target per rank (L2 is 126 MB)",
                        "setup_s": round(t_setup, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
