@@ -283,6 +283,25 @@ def run_native(args):
         raise SystemExit("bench.py (native arm) needs a B200: there is no CPU fallback for the hot path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1:
+        # pin this rank to the CPUs next to its GPU BEFORE any pinned host buffer is allocated: first touch
+        # then places the staging memory on the GPU's NUMA node (matters for the host-buffer e2e legs)
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(local).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            cpus = {64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = len(cpus)
+        except Exception:
+            numa = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -583,7 +602,7 @@ def run_native(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "n_loci": n, "density": density, "pairs_per_step": float(n) * float(n), "loss_mode": args.loss_mode,
-                       "parallelism": f"rows{world}" if world > 1 else ("single" if not args.emulate_world else f"rank0-of-{args.emulate_world} (emulated, NOT a bench line)"), "rows_per_rank": nloc, "exchange": transport, "exchange_ms": exch_ms,
+                       "parallelism": f"rows{world}" if world > 1 else ("single" if not args.emulate_world else f"rank0-of-{args.emulate_world} (emulated, NOT a bench line)"), "rows_per_rank": nloc, "cpus_near_gpu": numa, "exchange": transport, "exchange_ms": exch_ms,
                        "timed_attempts": attempts, "l2": f"no flush: each step streams {target_bytes / 1e6:.0f} MB of target per rank (L2 is 126 MB)",
                        "setup_s": round(t_setup, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
