@@ -2,10 +2,15 @@
 
 Rank r owns target rows ``[r*ceil(N/G), (r+1)*ceil(N/G))`` x all N columns.  The GNN is
 replicated, so every rank already holds identical N x 3 coordinates; per step each rank runs
-the fused kernel on its block and ONE all-reduce(sum) of the packed f64 buffer
-``[8 moments | 3N gradient]`` (<= 1.2 MB at 50k loci: latency-bound) combines them.
-Host-side logic is backend-agnostic: the gloo tests run it on CPU tensors with a stand-in
-for the kernel.
+the fused kernel on its block and ONE exchange combines the partials (latency-bound: <= 0.6 MB
+per rank at 50k loci):
+
+* :class:`P2PShardedPairLoss` (default on CUDA): the library's one-shot all-reduce kernel over
+  NVLink peer memory (csrc/comm.cu), partials ``[8 x f64 moments | 3N x f32 gradient]`` in a
+  symmetric buffer;
+* :class:`ShardedPairLoss`: one NCCL / gloo ``all_reduce`` of the packed f64 buffer
+  ``[8 moments | 3N gradient]``.  Backend-agnostic: the gloo tests run it on CPU tensors with a
+  stand-in for the kernel.
 """
 from __future__ import annotations
 

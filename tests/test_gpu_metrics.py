@@ -73,3 +73,18 @@ def test_final_dscc_within_1e3_of_oracle_on_chr19(golden, cls, mode, max_steps):
         got = metrics.dscc(gm.get_model(gdata.x.float(), gdata.edge_index), target)
     assert abs(got - want) < tol, (got, want, tol, len(h_g), len(h_o))
     assert abs(h_g[-1] - h_o[-1]) / abs(h_o[-1]) < (1e-2 if len(h_o) < max_steps else 1e-1)
+
+
+def test_example_pipeline_runs_end_to_end(monkeypatch):
+    """examples/chr19_gat_hic.py: list -> matrix -> KR -> graph -> GAT training -> dSCC, all on the GPU."""
+    import importlib.util
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("chr19_example", os.path.join(root, "examples", "chr19_gat_hic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(sys, "argv", ["chr19_gat_hic.py", "--steps", "60"])
+    hist, coords = mod.main()
+    assert len(hist) <= 60 and hist[-1] < hist[0] and coords.shape == (58, 3) and bool(torch.isfinite(coords).all())
