@@ -382,46 +382,59 @@ __global__ void __launch_bounds__(256) gat_bwd_node_kernel(const int32_t* __rest
 
 // ------------------------------------------------------------------ GAT backward, step 3 (parameter grads)
 // datt_l[c] = sum_j d_a_src[j,h(c)] xl[j,c] ; datt_r[c] = sum_j d_a_dst[j,h(c)] xl[j,c] ; dbias[c] = sum_i g[i,c]
-// stage A: per 64-row chunk partial sums (thread per channel, coalesced); stage B: the last CTA
-// adds the chunk partials in fixed order (deterministic).
-constexpr int kParamRows = 64;
-__global__ void __launch_bounds__(256) gat_bwd_param_kernel(const float* __restrict__ xl, const float* __restrict__ gout,
+// stage A: kParamCtas CTAs stride over the rows (float4 per thread, two rows in flight) and keep their sums in
+// registers; partials are stored TRANSPOSED, part[(k*F + c) * nblk + blk], so that stage B -- one warp per
+// output value, lanes striding the nblk partials, fixed order -- reads them coalesced.  Deterministic.
+constexpr int kParamRows = 64;   // kept for the workspace formula (upper bound of the partial count)
+constexpr int kParamCtas = 148 * 2;
+__global__ void __launch_bounds__(128) gat_bwd_param_kernel(const float* __restrict__ xl, const float* __restrict__ gout,
                                                             const float* __restrict__ d_a_src, const float* __restrict__ d_a_dst,
-                                                            int n, int H, int C, float* __restrict__ part, unsigned* __restrict__ counter,
-                                                            float* __restrict__ datt_l, float* __restrict__ datt_r, float* __restrict__ dbias) {
-    const int F = H * C;
-    const int chunk = blockIdx.x, nchunks = gridDim.x;
-    const int r0 = chunk * kParamRows, r1 = min(r0 + kParamRows, n);
-    for (int c = threadIdx.x; c < F; c += blockDim.x) {
+                                                            int n, int H, int C, float* __restrict__ part) {
+    const int F = H * C, nblk = gridDim.x, blk = blockIdx.x;
+    for (int c = threadIdx.x * 4; c < F; c += blockDim.x * 4) {
         const int h = c / C;
-        float sl = 0.f, sr = 0.f, sb = 0.f;
-        for (int r = r0; r < r1; ++r) {
-            const float x = xl[(size_t)r * F + c];
-            sl = fmaf(d_a_src[r * H + h], x, sl);
-            sr = fmaf(d_a_dst[r * H + h], x, sr);
-            sb += gout[(size_t)r * F + c];
+        float4 sl = make_float4(0.f, 0.f, 0.f, 0.f), sr = sl, sb = sl;
+        int r = blk;
+        for (; r + nblk < n; r += 2 * nblk) {
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(xl + (size_t)r * F + c));
+            const float4 x1 = __ldg(reinterpret_cast<const float4*>(xl + (size_t)(r + nblk) * F + c));
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gout + (size_t)r * F + c));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gout + (size_t)(r + nblk) * F + c));
+            const float s0 = d_a_src[r * H + h], t0 = d_a_dst[r * H + h], s1 = d_a_src[(r + nblk) * H + h], t1 = d_a_dst[(r + nblk) * H + h];
+            fma4(sl, s0, x0); fma4(sr, t0, x0); sb.x += g0.x; sb.y += g0.y; sb.z += g0.z; sb.w += g0.w;
+            fma4(sl, s1, x1); fma4(sr, t1, x1); sb.x += g1.x; sb.y += g1.y; sb.z += g1.z; sb.w += g1.w;
         }
-        float* p = part + (size_t)chunk * 3 * F;
-        __stcg(p + c, sl);
-        __stcg(p + F + c, sr);
-        __stcg(p + 2 * F + c, sb);
+        if (r < n) {
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(xl + (size_t)r * F + c));
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gout + (size_t)r * F + c));
+            fma4(sl, d_a_src[r * H + h], x0); fma4(sr, d_a_dst[r * H + h], x0);
+            sb.x += g0.x; sb.y += g0.y; sb.z += g0.z; sb.w += g0.w;
+        }
+        const float vl[4] = {sl.x, sl.y, sl.z, sl.w}, vr[4] = {sr.x, sr.y, sr.z, sr.w}, vb[4] = {sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            part[((size_t)(0 * F + c + q)) * nblk + blk] = vl[q];
+            part[((size_t)(1 * F + c + q)) * nblk + blk] = vr[q];
+            part[((size_t)(2 * F + c + q)) * nblk + blk] = vb[q];
+        }
     }
-    __threadfence();
-    __syncthreads();
-    __shared__ unsigned s_ticket;
-    if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
-    __syncthreads();
-    if (s_ticket != (unsigned)(nchunks - 1)) return;
-    __threadfence();
-    for (int c = threadIdx.x; c < 3 * F; c += blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < nchunks; ++k) s += __ldcg(part + (size_t)k * 3 * F + c);
-        if (c < F) datt_l[c] = s;
-        else if (c < 2 * F) datt_r[c - F] = s;
-        else dbias[c - 2 * F] = s;
-    }
-    if (threadIdx.x == 0) *counter = 0u;  // self-reset for the next call
 }
+
+__global__ void __launch_bounds__(256) gat_bwd_param_reduce_kernel(const float* __restrict__ part, int nblk, int F,
+                                                                   float* __restrict__ datt_l, float* __restrict__ datt_r, float* __restrict__ dbias) {
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (o >= 3 * F) return;
+    float s = 0.f;
+    for (int k = lane; k < nblk; k += 32) s += part[(size_t)o * nblk + k];
+    s = warp_sum(s);
+    if (lane == 0) {
+        if (o < F) datt_l[o] = s;
+        else if (o < 2 * F) datt_r[o - F] = s;
+        else dbias[o - 2 * F] = s;
+    }
+}
+
+int param_ctas(int64_t n) { return (int)(n < kParamCtas ? n : kParamCtas); }
 
 bool supported(int H, int C) {
     const int F = H * C;
@@ -498,7 +511,7 @@ BwdLayout bwd_layout(int64_t n, int64_t nnz, int H, int C) {
     L.off_dsrc = L.off_dz + align_up(sizeof(float) * (size_t)nnz * H, 256);
     L.off_ddst = L.off_dsrc + align_up(sizeof(float) * (size_t)n * H, 256);
     L.off_part = L.off_ddst + align_up(sizeof(float) * (size_t)n * H, 256);
-    L.total = L.off_part + sizeof(float) * 3 * F * (size_t)L.nchunks;
+    L.total = L.off_part + sizeof(float) * 3 * F * (size_t)param_ctas(n);
     return L;
 }
 }  // namespace
@@ -525,12 +538,10 @@ extern "C" int hicgat_gat_bwd(const int32_t* rowptr, const int32_t* col, const i
         return HICGAT_ERR_WORKSPACE;
     }
     unsigned char* ws = static_cast<unsigned char*>(workspace);
-    unsigned* counter = reinterpret_cast<unsigned*>(ws + L.off_counter);
     float* dz = reinterpret_cast<float*>(ws + L.off_dz);
     float* dsrc = reinterpret_cast<float*>(ws + L.off_dsrc);
     float* ddst = reinterpret_cast<float*>(ws + L.off_ddst);
     float* part = reinterpret_cast<float*>(ws + L.off_part);
-    HICGAT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
     const unsigned grid = (unsigned)((n + kRowsPerCta - 1) / kRowsPerCta);
 #define CALL_EDGE(H, Q) gat_bwd_edge_kernel<H, Q><<<grid, 256, 0, stream>>>(rowptr, col, xl, a_src, a_dst, alpha, gout, slope, (int)n, dz, ddst)
     HICGAT_DISPATCH_HQ(heads, channels, CALL_EDGE);
@@ -540,8 +551,11 @@ extern "C" int hicgat_gat_bwd(const int32_t* rowptr, const int32_t* col, const i
     HICGAT_DISPATCH_HQ(heads, channels, CALL_NODE);
 #undef CALL_NODE
     HICGAT_CHECK_LAUNCH("gat_bwd_node_kernel");
-    gat_bwd_param_kernel<<<L.nchunks, 256, 0, stream>>>(xl, gout, dsrc, ddst, (int)n, heads, channels, part, counter, datt_l, datt_r, dbias);
+    const int nblk = param_ctas(n);
+    gat_bwd_param_kernel<<<nblk, 128, 0, stream>>>(xl, gout, dsrc, ddst, (int)n, heads, channels, part);
     HICGAT_CHECK_LAUNCH("gat_bwd_param_kernel");
+    gat_bwd_param_reduce_kernel<<<(3 * heads * channels + 7) / 8, 256, 0, stream>>>(part, nblk, heads * channels, datt_l, datt_r, dbias);
+    HICGAT_CHECK_LAUNCH("gat_bwd_param_reduce_kernel");
     return HICGAT_OK;
 }
 
@@ -562,7 +576,7 @@ extern "C" int hicgat_gat_logits(int64_t n, int heads, int channels, const float
 
 extern "C" size_t hicgat_gat_param_grads_workspace_bytes(int64_t n, int heads, int channels) {
     if (n <= 0 || !supported(heads, channels)) return 0;
-    return 256 + sizeof(float) * 3 * (size_t)heads * channels * (size_t)((n + kParamRows - 1) / kParamRows);
+    return 256 + sizeof(float) * 3 * (size_t)heads * channels * (size_t)param_ctas(n);
 }
 
 // datt_l[c] = sum_j d_a_src[j,h(c)] xl[j,c] ; datt_r[c] = sum_j d_a_dst[j,h(c)] xl[j,c] ; dbias[c] = sum_i g[i,c]
@@ -578,11 +592,11 @@ extern "C" int hicgat_gat_param_grads(int64_t n, int heads, int channels, const 
         return HICGAT_ERR_WORKSPACE;
     }
     unsigned char* ws = static_cast<unsigned char*>(workspace);
-    unsigned* counter = reinterpret_cast<unsigned*>(ws);
     float* part = reinterpret_cast<float*>(ws + 256);
-    HICGAT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
-    const int nchunks = (int)((n + kParamRows - 1) / kParamRows);
-    gat_bwd_param_kernel<<<nchunks, 256, 0, stream>>>(xl, gout, d_a_src, d_a_dst, (int)n, heads, channels, part, counter, datt_l, datt_r, dbias);
+    const int nblk = param_ctas(n);
+    gat_bwd_param_kernel<<<nblk, 128, 0, stream>>>(xl, gout, d_a_src, d_a_dst, (int)n, heads, channels, part);
     HICGAT_CHECK_LAUNCH("gat_bwd_param_kernel");
+    gat_bwd_param_reduce_kernel<<<(3 * heads * channels + 7) / 8, 256, 0, stream>>>(part, nblk, heads * channels, datt_l, datt_r, dbias);
+    HICGAT_CHECK_LAUNCH("gat_bwd_param_reduce_kernel");
     return HICGAT_OK;
 }
