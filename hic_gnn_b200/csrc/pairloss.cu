@@ -23,17 +23,23 @@
 //   A/B measurements and as the path used when a tensor map cannot be encoded.
 #include <cuda.h>  // CUtensorMap (types only; the encoder is resolved through cudart at run time)
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hicgat {
 namespace {
 
-constexpr int kWarps = 8;                 // consumer warps
+#ifndef HICGAT_PAIR_WARPS
+#define HICGAT_PAIR_WARPS 8                // experiments: 4 warps x 4 CTAs per SM
+#endif
+constexpr int kWarps = HICGAT_PAIR_WARPS; // consumer warps
+constexpr int kCtasPerSm = 16 / kWarps;   // 16 resident warps of 128 registers per SM
 constexpr int kThreads = kWarps * 32;     // variant 1 block size
 constexpr int kCols = 128;                // columns per CTA strip (32 lanes x 4)
 constexpr int kU = 8;                     // rows per warp per group / tile
 constexpr int kNM = HICGAT_PAIR_NMOM;
-constexpr int kCtaSlots = 148 * 2;        // resident CTAs of the TMA kernel (2 per SM)
+constexpr int kCtaSlots = 148 * kCtasPerSm;  // resident CTAs of the TMA kernel (2 per SM)
 constexpr int kTileRows = kWarps * kU;    // 64 rows per CTA tile step (8 per warp)
 constexpr int kStages = 3;                // TMA slots per warp
 constexpr int kSubTileBytes = kU * kCols * 4;               // 4096: one warp's 8 rows x 128 columns
@@ -43,6 +49,28 @@ constexpr int kTmaSmem = kWarps * kStages * kSlotBytes + 128;  // 104576 B: two 
 // which upper-triangle statistics are accumulated
 constexpr uint32_t kMomFull = HICGAT_PAIR_MOMENTS;          // everything (sum t, sum t^2, sum |d-t| too)
 constexpr uint32_t kMomLight = HICGAT_PAIR_MOMENTS_D;       // sum d, sum d^2, sum d t, sum (d-t)^2 only
+
+// Debug timeline (scratch builds with -DHICGAT_TRACE only; never in the shipped library): thread 0 of
+// every CTA stamps %globaltimer at fixed points of pairloss_tma_kernel into g_trace[cta][8].
+#ifdef HICGAT_TRACE
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define HICGAT_TR(k)                                                                                         \
+    do {                                                                                                     \
+        if (threadIdx.x == 0 && g_trace) g_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (k)] = gtimer(); \
+    } while (0)
+#define HICGAT_TRV(k, v)                                                                                     \
+    do {                                                                                                     \
+        if (threadIdx.x == 0 && g_trace) g_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (k)] = (v); \
+    } while (0)
+#else
+#define HICGAT_TR(k) do { } while (0)
+#define HICGAT_TRV(k, v) do { } while (0)
+#endif
 
 struct Acc {
     f2 gx[2], gy[2], gz[2];          // column-side gradient, 2 column pairs
@@ -167,11 +195,8 @@ struct Params {
     double* moments;
     float* grad;
     double* grad64;        // optional f64 copy of grad (packed all-reduce buffer)
-    float* gpart;          // [nchunks][nstrips][384]
-    double* mpart;         // [nchunks*nstrips][kNM]
-    double* spart;         // [nstrips][kNM] per-strip moment partials
-    unsigned* strip_count; // [nstrips]
-    unsigned* done_count;  // [1]
+    float* gpart;          // [nchunks][nstrips][384]  per-CTA gradient partials
+    double* mpart;         // [nchunks*nstrips][kNM]   per-CTA moment partials
 };
 
 struct ColumnRegs {
@@ -268,7 +293,6 @@ __device__ __forceinline__ int chunk_rows(const Params& P, int strip, int chunk,
 struct CombineSmem {
     float g[kWarps][kCols * 3 + 4];
     double m[kWarps][kNM];
-    unsigned ticket[2];
 };
 
 // warp-level part of the CTA combine: park this warp's gradients / moments in shared memory
@@ -313,11 +337,21 @@ __device__ __forceinline__ void park_warp(const Acc& a, CombineSmem& S, int warp
     }
 }
 
-// CTA-level combine + cross-CTA fixed-order reduction.  Called by ALL threads of the block after
-// a __syncthreads() that follows park_warp(); nthreads = blockDim.x.
+// Programmatic dependent launch: the producer kernels allow pairloss_combine_kernel to be scheduled as soon
+// as their last CTA has STARTED; its blocks then sit resident (launch latency, instruction fetch and
+// parameter loads done) in griddepcontrol.wait until the producer grid has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// CTA-level combine.  Called by ALL threads of the block after a __syncthreads() that follows
+// park_warp(); nthreads = blockDim.x.  The CTA only STORES its partial (f32 gradient of its 128
+// columns, f64 moments) at slot chunk * nstrips + strip and exits: no fence, no ticket, no atomics.
+// A streaming CTA slot that sits in a publish round trip (fence + atomic under a saturated memory
+// system: ~3 us, measured per CTA with %globaltimer) streams nothing, and row blocks of a few thousand
+// rows have only 2-5 items per slot; the cross-CTA sums are done by pairloss_combine_kernel, launched
+// right behind on the same stream (the kernel boundary is the release / acquire).
 template <uint32_t MODE>
-__device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int strip, int chunk, int count, int tid, int nthreads) {
-    const int n = P.n;
+__device__ __forceinline__ void publish_cta(const Params& P, CombineSmem& S, int strip, int chunk, int tid, int nthreads) {
     const int cta = chunk * P.nstrips + strip;
     if constexpr ((MODE & 3u) != 0) {
         float* gp = P.gpart + (size_t)cta * (kCols * 3);
@@ -334,93 +368,115 @@ __device__ __forceinline__ void finish_cta(const Params& P, CombineSmem& S, int 
         for (int w = 0; w < kWarps; ++w) s += S.m[w][tid];
         __stcg(P.mpart + (size_t)cta * kNM + tid, s);
     }
-    // Publish: the block barrier orders every thread's partial stores before thread 0's fence,
-    // and the fence is cumulative, so ONE membar per CTA suffices (a per-thread __threadfence()
-    // costs every warp a memory barrier on the critical path of the CTA's epilogue).
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        S.ticket[0] = atomicAdd(P.strip_count + strip, 1u);
-        __threadfence();  // acquire side for the last CTA of the strip
-    }
-    __syncthreads();
-    if (S.ticket[0] != (unsigned)(count - 1)) return;
-    if (tid == 0) P.strip_count[strip] = 0u;  // leave the counters zeroed for the next call (HICGAT_PAIR_WS_CLEAN)
-    // ---- last CTA of this column strip: add the strip's row-chunk partials in chunk order
-    if constexpr ((MODE & 3u) != 0) {
-        const float scale = ((MODE & 3u) == HICGAT_PAIR_GRAD_MSE) ? P.c_mse
-                            : ((MODE & 3u) == HICGAT_PAIR_GRAD_L1) ? P.c_l1 : 1.f;
-        for (int i = tid; i < kCols * 3; i += nthreads) {
-            const float* src = P.gpart + (size_t)strip * (kCols * 3) + i;
+}
+
+// Cross-CTA sums in a FIXED order (bit-reproducible).  Blocks 0 .. nstrips-1: the strip's gradient =
+// its row-chunk partials added in chunk order in f64, scaled, rounded once to f32.  Block nstrips: the
+// moments = every CTA's f64 partial, thread t taking slots t, t+256, ... (slots of chunks a strip does
+// not have are skipped), then lanes, then warps.
+constexpr int kCombineThreads = 256;
+// `npass` = 2 under programmatic dependent launch: the blocks become resident while the producer's last
+// wave is still streaming, and the producer has pushed everything else -- including this kernel's
+// instructions -- out of L2 (400 MB+ go through 126 MB), so the first execution of the body after the
+// wait would pay one DRAM round trip per instruction-cache line (measured: 3-8 us for ~1 us of work).
+// Pass 0 therefore runs the SAME code on whatever the buffers hold, stores nothing, and leaves the
+// instruction cache, the TLB entries and the parameter loads warm; pass 1 follows the wait.
+__global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const Params P, const float scale, const int want_grad, const int npass) {
+    const int tid = threadIdx.x;
+    const int total = P.r1 - P.r0;
+    __shared__ double s_m[kCombineThreads / 32][kNM];
+#ifdef HICGAT_TRACE
+    unsigned long long* ctr = (g_trace && tid == 0 && ((int)blockIdx.x == 0 || (int)blockIdx.x == P.nstrips)) ? g_trace + (size_t)(8190 + ((int)blockIdx.x == 0 ? 0 : 1)) * 8 : nullptr;
+    if (ctr) ctr[0] = gtimer();
+#endif
+#pragma unroll 1
+    for (int pass = 0; pass < npass; ++pass) {
+        const bool live = pass == npass - 1;
+        if (live) {
+            pdl_wait();  // no-op when launched without the programmatic-serialization attribute
+#ifdef HICGAT_TRACE
+            if (ctr) ctr[1] = gtimer();
+#endif
+        }
+        if ((int)blockIdx.x < P.nstrips) {
+            if (!want_grad) return;
+            const int strip = blockIdx.x;
+            const int off = (P.stagger && ((strip / 148) & 1)) ? (P.rb >> 1) : 0;
+            const int count = (total + off + P.rb - 1) / P.rb;
+            // elements tid and tid + 256 of the strip's 384, 8 chunks per round: 16 independent loads in flight,
+            // added in chunk order (out-of-range terms are +0.0, which leaves the sum unchanged)
+            const int i0 = tid, i1 = tid + kCombineThreads;
+            const bool has1 = i1 < kCols * 3;
+            const float* src0 = P.gpart + (size_t)strip * (kCols * 3) + i0;
+            const float* src1 = src0 + (has1 ? kCombineThreads : 0);
             const size_t stride = (size_t)P.nstrips * (kCols * 3);
-            double s = 0.0;
-            int c = 0;
-            for (; c + 4 <= count; c += 4) {  // 4 independent loads in flight, summed in chunk order
-                const float v0 = __ldcg(src + (size_t)c * stride), v1 = __ldcg(src + (size_t)(c + 1) * stride);
-                const float v2 = __ldcg(src + (size_t)(c + 2) * stride), v3 = __ldcg(src + (size_t)(c + 3) * stride);
-                s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+            double s0 = 0.0, s1 = 0.0;
+            for (int c = 0; c < count; c += 8) {
+                float v0[8], v1[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const bool in = c + k < count;
+                    v0[k] = in ? __ldcg(src0 + (size_t)(c + k) * stride) : 0.f;
+                    v1[k] = (in && has1) ? __ldcg(src1 + (size_t)(c + k) * stride) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    s0 += (double)v0[k];
+                    s1 += (double)v1[k];
+                }
             }
-            for (; c < count; ++c) s += (double)__ldcg(src + (size_t)c * stride);
-            const int col = strip * kCols + i / 3;
-            if (col < n) {
-                const double v = s * (double)scale;
-                if (P.grad) P.grad[(size_t)strip * kCols * 3 + i] = (float)v;
-                if (P.grad64) P.grad64[(size_t)strip * kCols * 3 + i] = (double)(float)v;
+            auto put = [&](int e, double s) {
+                if (live && strip * kCols + e / 3 < P.n) {
+                    const double v = s * (double)scale;
+                    if (P.grad) P.grad[(size_t)strip * kCols * 3 + e] = (float)v;
+                    if (P.grad64) P.grad64[(size_t)strip * kCols * 3 + e] = (double)(float)v;
+                }
+            };
+            put(i0, s0);
+            if (has1) put(i1, s1);
+        } else {
+            double m[kNM];
+#pragma unroll
+            for (int k = 0; k < kNM; ++k) m[k] = 0.0;
+            // every strip has the chunks 0 .. nchunks-2; only the last chunk row has holes (unstaggered strips)
+            const int nfull = P.nstrips * (P.nchunks - 1);
+#pragma unroll 4
+            for (int sl = tid; sl < nfull; sl += kCombineThreads) {
+#pragma unroll
+                for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.mpart + (size_t)sl * kNM + k);
+            }
+            for (int st = tid; st < P.nstrips; st += kCombineThreads) {
+                const int off = (P.stagger && ((st / 148) & 1)) ? (P.rb >> 1) : 0;
+                if (P.nchunks - 1 < (total + off + P.rb - 1) / P.rb) {
+#pragma unroll
+                    for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.mpart + (size_t)(nfull + st) * kNM + k);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kNM; ++k) m[k] = warp_sum(m[k]);
+            __syncthreads();  // s_m of the previous pass has been read
+            if ((tid & 31) == 0) {
+#pragma unroll
+                for (int k = 0; k < kNM; ++k) s_m[tid >> 5][k] = m[k];
+            }
+            __syncthreads();
+            if (live && tid < kNM) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < kCombineThreads / 32; ++w) s += s_m[w][tid];
+                P.moments[tid] = s;
             }
         }
     }
-    if (tid < kNM) {  // the strip's moments -> one partial per strip (loads batched, added in chunk order)
-        const double* src = P.mpart + (size_t)strip * kNM + tid;
-        const size_t stride = (size_t)P.nstrips * kNM;
-        double s = 0.0;
-        int c = 0;
-        for (; c + 4 <= count; c += 4) {
-            const double v0 = __ldcg(src + (size_t)c * stride), v1 = __ldcg(src + (size_t)(c + 1) * stride);
-            const double v2 = __ldcg(src + (size_t)(c + 2) * stride), v3 = __ldcg(src + (size_t)(c + 3) * stride);
-            s += v0; s += v1; s += v2; s += v3;
-        }
-        for (; c < count; ++c) s += __ldcg(src + (size_t)c * stride);
-        __stcg(P.spart + (size_t)strip * kNM + tid, s);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        S.ticket[1] = atomicAdd(P.done_count, 1u);
-        __threadfence();
-    }
-    __syncthreads();
-    if (S.ticket[1] != (unsigned)(P.nstrips - 1)) return;
-    if (tid == 0) *P.done_count = 0u;
-    // ---- last strip to finish: f64 reduction of the per-strip moment partials in a FIXED order
-    // (thread t takes strips t, t+256, ...; then lanes, then warps): the whole CTA works on it,
-    // because this is the serial tail of the kernel
-    double m[kNM];
-#pragma unroll
-    for (int k = 0; k < kNM; ++k) m[k] = 0.0;
-    if (tid < kThreads) {
-        for (int st = tid; st < P.nstrips; st += kThreads) {
-#pragma unroll
-            for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.spart + (size_t)st * kNM + k);
-        }
-#pragma unroll
-        for (int k = 0; k < kNM; ++k) m[k] = warp_sum(m[k]);
-        if ((tid & 31) == 0) {
-#pragma unroll
-            for (int k = 0; k < kNM; ++k) S.m[tid >> 5][k] = m[k];
-        }
-    }
-    __syncthreads();
-    if (tid < kNM) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += S.m[w][tid];
-        P.moments[tid] = s;
-    }
+#ifdef HICGAT_TRACE
+    if (ctr) ctr[2] = gtimer();
+#endif
 }
 
 // ------------------------------------------------------------------ variant 1: per-lane streaming loads
 template <uint32_t MODE>
-__global__ void __launch_bounds__(kThreads, 2) pairloss_ldg_kernel(const Params P) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_ldg_kernel(const Params P) {
+    pdl_launch_dependents();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_xy = reinterpret_cast<float4*>(smem_raw);                          // [rb] (x,x,y,y)
     float2* s_z = reinterpret_cast<float2*>(smem_raw + sizeof(float4) * P.rb);   // [rb] (z,z)
@@ -469,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_ldg_kernel(const Params 
     }
     park_warp<MODE>(a, S, warp, lane);
     __syncthreads();
-    finish_cta<MODE>(P, S, strip, chunk, count, threadIdx.x, kThreads);
+    publish_cta<MODE>(P, S, strip, chunk, threadIdx.x, kThreads);
 }
 
 // ------------------------------------------------------------------ implicit target, dense part (compute only)
@@ -479,7 +535,8 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_ldg_kernel(const Params 
 // all (FP32 / MUFU bound instead of HBM bound); pairloss_csr_fix_kernel then corrects the nnz pairs
 // that do carry a contact.  Same decomposition, arithmetic and reductions as the streamed kernels.
 template <uint32_t MODE>
-__global__ void __launch_bounds__(kThreads, 2) pairloss_const_kernel(const Params P) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_const_kernel(const Params P) {
+    pdl_launch_dependents();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_xy = reinterpret_cast<float4*>(smem_raw);                          // [rb] (x,x,y,y)
     float2* s_z = reinterpret_cast<float2*>(smem_raw + sizeof(float4) * P.rb);   // [rb] (z,z)
@@ -527,7 +584,7 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_const_kernel(const Param
     }
     park_warp<MODE>(a, S, warp, lane);
     __syncthreads();
-    finish_cta<MODE>(P, S, strip, chunk, count, threadIdx.x, kThreads);
+    publish_cta<MODE>(P, S, strip, chunk, threadIdx.x, kThreads);
 }
 
 // Correction of the pairs that carry a contact (CSR rows [r0, r1), warp per row, ROW-side sums: by the
@@ -687,7 +744,8 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 // per stage for the warp's rows of tile t and refills the slot right after the warp has consumed
 // it -- no producer warp, no empty barriers, no cross-warp synchronisation in the main loop.
 template <uint32_t MODE>
-__global__ void __launch_bounds__(kThreads, 2) pairloss_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params P) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params P) {
+    pdl_launch_dependents();
     extern __shared__ unsigned char smem_raw[];
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     __shared__ __align__(8) uint64_t full_bar[kWarps][kStages];
@@ -696,6 +754,10 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_tma_kernel(const __grid_
     const int strip = blockIdx.x, chunk = blockIdx.y;
     const int n = P.n;
     int row_begin, nrows;
+    HICGAT_TR(0);
+#ifdef HICGAT_TRACE
+    { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); HICGAT_TRV(6, (unsigned long long)smid); HICGAT_TRV(7, 0ull); }
+#endif
     const int count = chunk_rows(P, strip, chunk, row_begin, nrows);
     if (chunk >= count) return;  // unstaggered strips leave the extra chunk slot empty
     const int ntiles = (nrows + kTileRows - 1) / kTileRows;
@@ -746,6 +808,9 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_tma_kernel(const __grid_
         const bool refill = t + kStages < ntiles;
         const float xi_next = refill ? xi_fetch(t + kStages) : 0.f;   // in flight during the compute below
         mbar_wait(&full_bar[warp][s], (uint32_t)(use & 1));
+#ifdef HICGAT_TRACE
+        if (t == 0) HICGAT_TR(1);
+#endif
         const uint32_t slot = wring_s + s * kSlotBytes;
         const XiAddr xi{slot + kSubTileBytes, slot + kSubTileBytes + kU * 16};
         const int rows_here = max(0, min(kU, nrows - (t * kTileRows + wrow)));
@@ -759,11 +824,14 @@ __global__ void __launch_bounds__(kThreads, 2) pairloss_tma_kernel(const __grid_
             xi_store(s, xi_next);
         }
     }
+    HICGAT_TR(2);
     __syncthreads();  // all rings drained: the dynamic shared memory is reused for the combine
     CombineSmem& S = *reinterpret_cast<CombineSmem*>(ring);
     park_warp<MODE>(a, S, warp, lane);
     __syncthreads();
-    finish_cta<MODE>(P, S, strip, chunk, count, threadIdx.x, kThreads);
+    publish_cta<MODE>(P, S, strip, chunk, threadIdx.x, kThreads);
+    HICGAT_TR(3);
+    HICGAT_TR(5);
 }
 
 // ------------------------------------------------------------------ materialising variant
@@ -801,6 +869,7 @@ __global__ void pairdist_bwd_kernel(const float* __restrict__ coords, int n, con
 int g_rows_per_cta = 0;
 int g_stagger = 1;
 int g_variant = 0;  // 0 = TMA ring (default), 1 = per-lane streaming loads
+const bool g_pdl = []() { const char* e = getenv("HICGAT_NO_PDL"); return !(e && e[0] == '1'); }();  // A/B: plain launch of the combine kernel
 
 int pick_rows_per_cta(int64_t nrows, int nstrips, int variant) {
     if (g_rows_per_cta > 0) return variant == 0 ? (g_rows_per_cta + kTileRows - 1) / kTileRows * kTileRows : g_rows_per_cta;
@@ -840,7 +909,8 @@ int pick_rows_per_cta(int64_t nrows, int nstrips, int variant) {
 
 struct Layout {
     int nstrips, rb, nchunks, stagger;
-    size_t off_counts, off_gpart, off_mpart, off_spart, total;
+    size_t nslots;           // partial slots in gpart / mpart = nstrips * nchunks
+    size_t off_gpart, off_mpart, total;
 };
 
 Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant) {
@@ -853,11 +923,10 @@ Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant) {
     // stagger (chunk_rows): only where a second CTA slot per SM is filled in the first wave
     L.stagger = (variant == 0 && g_stagger && L.nstrips > 148 && L.nchunks >= 2) ? 1 : 0;
     if (L.stagger) L.nchunks = (int)((nrows + L.rb / 2 + L.rb - 1) / L.rb);
-    L.off_counts = 0;
-    L.off_spart = align_up(sizeof(unsigned) * (size_t)(L.nstrips + 1), 256);
-    L.off_mpart = L.off_spart + align_up(sizeof(double) * kNM * (size_t)L.nstrips, 256);
-    L.off_gpart = L.off_mpart + align_up(sizeof(double) * kNM * (size_t)L.nstrips * L.nchunks, 256);
-    L.total = L.off_gpart + sizeof(float) * (size_t)kCols * 3 * L.nstrips * L.nchunks;
+    L.nslots = (size_t)L.nstrips * L.nchunks;
+    L.off_mpart = 0;
+    L.off_gpart = L.off_mpart + align_up(sizeof(double) * kNM * L.nslots, 256);
+    L.total = L.off_gpart + sizeof(float) * (size_t)kCols * 3 * L.nslots;
     return L;
 }
 
@@ -890,6 +959,27 @@ bool make_target_map(CUtensorMap* map, const float* target, int64_t pitch, int64
 }
 
 template <uint32_t MODE>
+cudaError_t launch_combine(const Params& P, cudaStream_t stream) {
+    const float scale = ((MODE & 3u) == HICGAT_PAIR_GRAD_MSE) ? P.c_mse : ((MODE & 3u) == HICGAT_PAIR_GRAD_L1) ? P.c_l1 : 1.f;
+    const int want_grad = (MODE & 3u) != 0 ? 1 : 0;
+    if (g_pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(P.nstrips + 1);
+        cfg.blockDim = dim3(kCombineThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, pairloss_combine_kernel, P, scale, want_grad, 2);
+    }
+    pairloss_combine_kernel<<<P.nstrips + 1, kCombineThreads, 0, stream>>>(P, scale, want_grad, 1);
+    return cudaGetLastError();
+}
+
+template <uint32_t MODE>
 cudaError_t launch_mode(int variant, const CUtensorMap& map, const Params& P, dim3 grid, cudaStream_t stream) {
     if (variant == 0) {
         static bool attr_set = false;  // opt in to > 48 KB dynamic shared memory once per instantiation
@@ -903,13 +993,21 @@ cudaError_t launch_mode(int variant, const CUtensorMap& map, const Params& P, di
         const size_t smem = (sizeof(float4) + sizeof(float2)) * (size_t)P.rb;
         pairloss_ldg_kernel<MODE><<<grid, kThreads, smem, stream>>>(P);
     }
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_combine<MODE>(P, stream);
 }
 
 }  // namespace
 }  // namespace hicgat
 
 using namespace hicgat;
+
+#ifdef HICGAT_TRACE
+extern "C" __attribute__((visibility("default"))) int hicgat_debug_set_trace(unsigned long long* buf) {
+    return cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int hicgat_pairloss_set_tuning(int rows_per_cta, int variant) {
     if (rows_per_cta != 0 && (rows_per_cta < 8 || rows_per_cta > 4096 || (rows_per_cta % 8) != 0)) {
@@ -944,8 +1042,7 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     HICGAT_REQUIRE(pitch >= n && (pitch % 4) == 0, "hicgat_pairloss_fwd_bwd: pitch %lld must be >= n and a multiple of 4", (long long)pitch);
     HICGAT_REQUIRE(aligned16(target), "hicgat_pairloss_fwd_bwd: target must be 16-byte aligned");  // NULL passes
     HICGAT_REQUIRE((mode & ~31u) == 0, "hicgat_pairloss_fwd_bwd: unknown mode bits 0x%x", mode);
-    const bool ws_clean = (mode & HICGAT_PAIR_WS_CLEAN) != 0;
-    mode &= ~HICGAT_PAIR_WS_CLEAN;
+    mode &= ~HICGAT_PAIR_WS_CLEAN;  // accepted for ABI compatibility; the workspace holds no state between calls
     if (mode & HICGAT_PAIR_MOMENTS) mode &= ~HICGAT_PAIR_MOMENTS_D;          // full moments include the light set
     if ((mode & HICGAT_PAIR_MOMENTS_D) && (mode & HICGAT_PAIR_GRAD_L1)) {     // the L1 value needs sum |d-t|: full set
         mode = (mode & ~HICGAT_PAIR_MOMENTS_D) | HICGAT_PAIR_MOMENTS;
@@ -960,7 +1057,6 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
         return HICGAT_ERR_WORKSPACE;
     }
     unsigned char* ws = static_cast<unsigned char*>(workspace);
-    if (!ws_clean) HICGAT_CUDA(cudaMemsetAsync(ws + L.off_counts, 0, sizeof(unsigned) * (size_t)(L.nstrips + 1), stream));
     if (r1 == r0) {  // empty row block: contributes nothing
         HICGAT_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * kNM, stream));
         if (grad) HICGAT_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * 3 * (size_t)n, stream));
@@ -970,11 +1066,9 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     Params P;
     P.coords = coords; P.target = target; P.pitch = pitch;
     P.n = (int)n; P.r0 = (int)r0; P.r1 = (int)r1; P.rb = L.rb; P.nstrips = L.nstrips; P.nchunks = L.nchunks; P.stagger = L.stagger;
+    P.fill = 0.f;
     P.c_mse = c_mse; P.c_l1 = c_l1; P.moments = moments; P.grad = grad; P.grad64 = grad64;
-    P.strip_count = reinterpret_cast<unsigned*>(ws + L.off_counts);
-    P.done_count = P.strip_count + L.nstrips;
     P.mpart = reinterpret_cast<double*>(ws + L.off_mpart);
-    P.spart = reinterpret_cast<double*>(ws + L.off_spart);
     P.gpart = reinterpret_cast<float*>(ws + L.off_gpart);
     dim3 grid(L.nstrips, L.nchunks);
     cudaError_t err = cudaSuccess;
@@ -991,7 +1085,7 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
         set_error("pairloss kernel launch failed: %s", cudaGetErrorString(err));
         return HICGAT_ERR_CUDA;
     }
-    count_launch();
+    count_launch(2);
     return HICGAT_OK;
 }
 
@@ -1038,6 +1132,8 @@ cudaError_t launch_sparse(const Params& P, dim3 grid, const int32_t* rowptr, con
     pairloss_const_kernel<MODE><<<grid, kThreads, smem, stream>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    e = launch_combine<MODE>(P, stream);
+    if (e != cudaSuccess) return e;
     pairloss_csr_fix_kernel<MODE><<<fix_ctas, 256, 0, stream>>>(P.coords, rowptr, col, tval, P.fill, P.n, P.r0, P.r1, P.c_mse, P.c_l1, P.moments, P.grad,
                                                                  P.grad64, part, counter);
     return cudaGetLastError();
@@ -1068,8 +1164,7 @@ static int pairloss_sparse_impl(const float* coords, const int32_t* rowptr, cons
     }
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     if (!ws_clean) {
-        HICGAT_CUDA(cudaMemsetAsync(ws + L.dense.off_counts, 0, sizeof(unsigned) * (size_t)(L.dense.nstrips + 1), stream));
-        HICGAT_CUDA(cudaMemsetAsync(ws + L.off_counter, 0, sizeof(unsigned), stream));
+        HICGAT_CUDA(cudaMemsetAsync(ws + L.off_counter, 0, sizeof(unsigned), stream));  // ticket of pairloss_csr_fix_kernel
     }
     if (r1 == r0) {
         HICGAT_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * kNM, stream));
@@ -1082,10 +1177,7 @@ static int pairloss_sparse_impl(const float* coords, const int32_t* rowptr, cons
     P.n = (int)n; P.r0 = (int)r0; P.r1 = (int)r1; P.rb = L.dense.rb; P.nstrips = L.dense.nstrips; P.nchunks = L.dense.nchunks; P.stagger = L.dense.stagger;
     P.fill = fill;
     P.c_mse = c_mse; P.c_l1 = c_l1; P.moments = moments; P.grad = grad; P.grad64 = grad64;
-    P.strip_count = reinterpret_cast<unsigned*>(ws + L.dense.off_counts);
-    P.done_count = P.strip_count + L.dense.nstrips;
     P.mpart = reinterpret_cast<double*>(ws + L.dense.off_mpart);
-    P.spart = reinterpret_cast<double*>(ws + L.dense.off_spart);
     P.gpart = reinterpret_cast<float*>(ws + L.dense.off_gpart);
     dim3 grid(L.dense.nstrips, L.dense.nchunks);
     double* part = reinterpret_cast<double*>(ws + L.off_part);
@@ -1104,7 +1196,7 @@ static int pairloss_sparse_impl(const float* coords, const int32_t* rowptr, cons
         set_error("sparse pairloss kernel launch failed: %s", cudaGetErrorString(err));
         return HICGAT_ERR_CUDA;
     }
-    count_launch(2);
+    count_launch(3);
     return HICGAT_OK;
 }
 

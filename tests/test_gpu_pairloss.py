@@ -154,7 +154,8 @@ def test_tuning_variants_agree():
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2])
-@pytest.mark.parametrize("n,r0,r1,rb", [(130, 0, 130, 0), (777, 3, 500, 0), (1000, 999, 1000, 0), (513, 64, 449, 0), (19500, 100, 1000, 128), (19300, 0, 700, 64)])
+@pytest.mark.parametrize("n,r0,r1,rb", [(130, 0, 130, 0), (777, 3, 500, 0), (1000, 999, 1000, 0), (513, 64, 449, 0), (19500, 100, 1000, 128), (19300, 0, 700, 64),
+                                        (40000, 5, 205, 0), (80000, 17, 60, 0)])
 def test_row_blocks_any_alignment_both_variants(variant, n, r0, r1, rb):
     """Row blocks that start / end at rows that are not multiples of the tile height, single-row
     blocks and blocks shorter than one tile, against an f64 torch evaluation of the same sums."""
