@@ -25,6 +25,8 @@ SIGNATURES = {
     "hicgat_pairloss_fwd_bwd": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _p, _sz, _p]),
     "hicgat_pairloss_fwd_bwd_packed": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _sz, _p]),
     "hicgat_pairloss_set_tuning": (C.c_int, [_i32, _i32]),
+    "hicgat_pairloss_set_schedule": (C.c_int, [_i32, _i32]),
+    "hicgat_pairloss_describe_schedule": (C.c_int, [_i64, _i64, _i64, _p, _i32]),
     "hicgat_pairloss_sparse_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "hicgat_pairloss_sparse_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _f32, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _p, _sz, _p]),
     "hicgat_allreduce_partials_p2p": (C.c_int, [_p, _p, _i32, _i32, _i64, _i64, _i32, _u32, _p, _p, _p, _p]),
@@ -98,6 +100,13 @@ _tuning_epoch = 0
 
 def tuning_epoch() -> int:
     return _tuning_epoch
+
+
+def set_pairloss_schedule(tail_depth: int = -1, tail_min_rows: int = 256) -> None:
+    """``hicgat_pairloss_set_schedule`` + invalidation of the cached workspaces."""
+    global _tuning_epoch
+    check(lib().hicgat_pairloss_set_schedule(tail_depth, tail_min_rows), "hicgat_pairloss_set_schedule")
+    _tuning_epoch += 1
 
 
 def set_pairloss_tuning(rows_per_cta: int = 0, variant: int = 0) -> None:

@@ -24,6 +24,9 @@
 #include <cuda.h>  // CUtensorMap (types only; the encoder is resolved through cudart at run time)
 
 #include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -184,12 +187,20 @@ __device__ __forceinline__ void pair_masked(Acc& a, int p, f2 xjx, f2 xjy, f2 xj
     }
 }
 
+// Row-chunk boundaries (offsets from r0) of the unstaggered [0] and the staggered [1] column strips.
+constexpr int kMaxChunks = 128;
+struct Schedule {
+    int count[2];
+    int bounds[2][kMaxChunks + 1];
+};
+
 struct Params {
     const float* coords;
     const float* target;  // points at row r0
     int64_t pitch;
     int n, r0, r1, rb, nstrips, nchunks;  // nchunks = grid.y = chunk slots per strip (staggered strips use one more than the others)
-    int stagger;                          // 1: strips with odd (strip / 148) start half a chunk early (see chunk_rows)
+    int stagger;                          // 1: strips with odd (strip / 148) use the second boundary table (see chunk_rows)
+    Schedule sch;
     float fill;                           // implicit-target kernel: wish distance of every non-edge pair
     float c_mse, c_l1;
     double* moments;
@@ -277,16 +288,21 @@ __device__ __forceinline__ void process_group(Acc& a, const ColumnRegs& c, const
 // Row range of (strip, chunk).  The two CTAs that share an SM start together and, with equal
 // chunks, would also finish together: both slots then sit in their epilogue / prologue at the same
 // time and the SM's share of HBM idles once per wave.  The first wave puts CTAs 148..295 (strips
-// 148..295 of chunk 0) into the second slot of every SM, so those strips get their chunk boundaries
-// shifted by half a chunk: their first item is half as long and the two slots stay half a period
-// apart for the rest of the kernel.  Returns the number of chunks of this strip.
+// 148..295 of chunk 0) into the second slot of every SM, so those strips use a second boundary table
+// whose first item is half as long: the two slots stay half a period apart for the rest of the
+// kernel.  Chunk lengths need not be equal: the host may shrink the last chunks of every strip so that
+// the items dispatched last are short (build_schedule).  Returns the number of chunks of this strip.
+__device__ __forceinline__ int strip_parity(const Params& P, int strip) { return (P.stagger && ((strip / 148) & 1)) ? 1 : 0; }
 __device__ __forceinline__ int chunk_rows(const Params& P, int strip, int chunk, int& row_begin, int& nrows) {
-    const int total = P.r1 - P.r0;
-    const int off = (P.stagger && ((strip / 148) & 1)) ? (P.rb >> 1) : 0;
-    const int count = (total + off + P.rb - 1) / P.rb;
-    const int start = max(0, chunk * P.rb - off), end = min(total, (chunk + 1) * P.rb - off);
+    const int par = strip_parity(P, strip);
+    const int count = P.sch.count[par];
+    int start = 0, end = 0;
+    if (chunk < count) {
+        start = P.sch.bounds[par][chunk];
+        end = P.sch.bounds[par][chunk + 1];
+    }
     row_begin = P.r0 + start;
-    nrows = max(0, end - start);
+    nrows = end - start;
     return count;
 }
 
@@ -383,7 +399,6 @@ constexpr int kCombineThreads = 256;
 // instruction cache, the TLB entries and the parameter loads warm; pass 1 follows the wait.
 __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const Params P, const float scale, const int want_grad, const int npass) {
     const int tid = threadIdx.x;
-    const int total = P.r1 - P.r0;
     __shared__ double s_m[kCombineThreads / 32][kNM];
 #ifdef HICGAT_TRACE
     unsigned long long* ctr = (g_trace && tid == 0 && ((int)blockIdx.x == 0 || (int)blockIdx.x == P.nstrips)) ? g_trace + (size_t)(8190 + ((int)blockIdx.x == 0 ? 0 : 1)) * 8 : nullptr;
@@ -401,8 +416,7 @@ __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const
         if ((int)blockIdx.x < P.nstrips) {
             if (!want_grad) return;
             const int strip = blockIdx.x;
-            const int off = (P.stagger && ((strip / 148) & 1)) ? (P.rb >> 1) : 0;
-            const int count = (total + off + P.rb - 1) / P.rb;
+            const int count = P.sch.count[strip_parity(P, strip)];
             // elements tid and tid + 256 of the strip's 384, 8 chunks per round: 16 independent loads in flight,
             // added in chunk order (out-of-range terms are +0.0, which leaves the sum unchanged)
             const int i0 = tid, i1 = tid + kCombineThreads;
@@ -438,18 +452,20 @@ __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const
             double m[kNM];
 #pragma unroll
             for (int k = 0; k < kNM; ++k) m[k] = 0.0;
-            // every strip has the chunks 0 .. nchunks-2; only the last chunk row has holes (unstaggered strips)
-            const int nfull = P.nstrips * (P.nchunks - 1);
+            // every strip has the chunks 0 .. cmin-1; the chunk rows above have holes (strips of the other parity)
+            const int cmin = min(P.sch.count[0], P.stagger ? P.sch.count[1] : P.sch.count[0]);
+            const int nfull = P.nstrips * cmin;
 #pragma unroll 4
             for (int sl = tid; sl < nfull; sl += kCombineThreads) {
 #pragma unroll
                 for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.mpart + (size_t)sl * kNM + k);
             }
-            for (int st = tid; st < P.nstrips; st += kCombineThreads) {
-                const int off = (P.stagger && ((st / 148) & 1)) ? (P.rb >> 1) : 0;
-                if (P.nchunks - 1 < (total + off + P.rb - 1) / P.rb) {
+            for (int ch = cmin; ch < P.nchunks; ++ch) {
+                for (int st = tid; st < P.nstrips; st += kCombineThreads) {
+                    if (ch < P.sch.count[strip_parity(P, st)]) {
 #pragma unroll
-                    for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.mpart + (size_t)(nfull + st) * kNM + k);
+                        for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.mpart + ((size_t)ch * P.nstrips + st) * kNM + k);
+                    }
                 }
             }
 #pragma unroll
@@ -909,20 +925,96 @@ int pick_rows_per_cta(int64_t nrows, int nstrips, int variant) {
 
 struct Layout {
     int nstrips, rb, nchunks, stagger;
+    Schedule sch;
     size_t nslots;           // partial slots in gpart / mpart = nstrips * nchunks
     size_t off_gpart, off_mpart, total;
 };
+
+int g_tail_depth = -1;    // -1 = library default; >= 0: hicgat_pairloss_set_schedule
+int g_tail_min_rows = 256;
+
+// Chunk lengths of one strip: `bulk` chunks of (about) rb rows followed by a tail of `depth` chunks that
+// halve each time (rb/2, rb/4, ... >= tail_min).  The hardware dispatches CTAs in (chunk, strip) order, so
+// the tail items are the ones that run last: the slots run dry within one SHORT item of each other
+// instead of one full-length item (measured on row blocks of 5-10k rows: the last 20-25 % of the kernel
+// ran with < 40 % of the CTA slots busy).  The staggered table starts with half a chunk and gets the
+// other half back right before the tail.  `unit` = rounding of the chunk lengths.
+void build_schedule(int64_t nrows, int rb, int depth, int tail_min, bool stagger, int unit, Schedule& S) {
+    auto round_up = [&](int64_t v) { return (int)((v + unit - 1) / unit * unit); };
+    int tail[16];
+    int ntail = 0;
+    int64_t tail_rows = 0;
+    for (int i = 1; i <= depth && ntail < 16; ++i) {
+        int t = round_up(rb >> i);
+        if (t < tail_min) t = round_up(tail_min);
+        if (t >= rb) break;                             // chunks are already at the minimum
+        if (tail_rows + t + rb / 2 > nrows) break;      // keep at least half a bulk chunk
+        tail[ntail++] = t;
+        tail_rows += t;
+        if (t == round_up(tail_min)) break;             // no point in repeating the minimum
+    }
+    const int64_t bulk_rows = nrows - tail_rows;
+    int nbulk = (int)((bulk_rows + rb - 1) / rb);
+    if (nbulk < 1) nbulk = 1;
+    const int blen = round_up((bulk_rows + nbulk - 1) / nbulk);
+    for (int par = 0; par < 2; ++par) {
+        int* b = S.bounds[par];
+        int c = 0;
+        int64_t pos = 0;
+        b[0] = 0;
+        auto push = [&](int64_t len, int64_t limit) {
+            if (len <= 0 || pos >= limit || c >= kMaxChunks) return;
+            pos = pos + len < limit ? pos + len : limit;
+            b[++c] = (int)pos;
+        };
+        const int half = (par == 1 && stagger) ? round_up(blen / 2) : 0;
+        if (half) push(half, bulk_rows);
+        for (int k = 0; k < nbulk; ++k) push(blen, bulk_rows);
+        if (pos < bulk_rows) push(bulk_rows - pos, bulk_rows);
+        for (int k = 0; k < ntail; ++k) push(tail[k], nrows);
+        if (pos < nrows) {  // out of table entries (never with rb >= nrows / 100): the last chunk takes the rest
+            if (c < kMaxChunks) ++c;
+            b[c] = (int)nrows;
+        }
+        S.count[par] = c > 0 ? c : 1;
+        if (c == 0) b[1] = (int)nrows;
+    }
+    if (!stagger) {
+        S.count[1] = S.count[0];
+        for (int k = 0; k <= kMaxChunks; ++k) S.bounds[1][k] = S.bounds[0][k];
+    }
+}
 
 Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant) {
     Layout L;
     L.nstrips = (int)((n + kCols - 1) / kCols);
     const int64_t nrows = r1 - r0;
     L.rb = pick_rows_per_cta(nrows, L.nstrips, variant);
-    L.nchunks = (int)((nrows + L.rb - 1) / L.rb);
-    if (L.nchunks < 1) L.nchunks = 1;
+    while ((nrows + L.rb - 1) / L.rb > kMaxChunks - 20) L.rb *= 2;  // boundary table size
+    const int uniform_chunks = (int)((nrows + L.rb - 1) / L.rb);
     // stagger (chunk_rows): only where a second CTA slot per SM is filled in the first wave
-    L.stagger = (variant == 0 && g_stagger && L.nstrips > 148 && L.nchunks >= 2) ? 1 : 0;
-    if (L.stagger) L.nchunks = (int)((nrows + L.rb / 2 + L.rb - 1) / L.rb);
+    L.stagger = (variant == 0 && g_stagger && L.nstrips > 148 && uniform_chunks >= 2) ? 1 : 0;
+    // Default tail: maps of up to 148 strips (no stagger, 1-3 items per CTA slot) end with three halving chunks
+    // down to 128 rows behind bulk chunks of at most 1024 rows (10k loci: 91.5 -> 85.3 us, measured with
+    // scripts/bench_pairloss_variants.py); staggered grids keep equal chunks (a tail measured +-1 % there).
+    int depth = 0, tail_min = g_tail_min_rows;
+    if (variant == 0) {
+        if (g_tail_depth >= 0) {
+            depth = g_tail_depth;
+        } else if (!L.stagger && nrows >= 2048 && g_rows_per_cta == 0) {
+            depth = 3;
+            tail_min = 128;
+            if (L.rb > 1024) L.rb = 1024;
+        }
+    }
+    memset(&L.sch, 0, sizeof(L.sch));
+    build_schedule(nrows > 0 ? nrows : 1, L.rb, depth, tail_min, L.stagger != 0, variant == 0 ? kTileRows : 8, L.sch);
+    L.nchunks = L.sch.count[0] > L.sch.count[1] ? L.sch.count[0] : L.sch.count[1];
+    // the per-lane-load and implicit-target kernels stage one chunk of x_i in shared memory: size = longest chunk
+    int longest = 0;
+    for (int par = 0; par < 2; ++par)
+        for (int k = 0; k < L.sch.count[par]; ++k) longest = std::max(longest, L.sch.bounds[par][k + 1] - L.sch.bounds[par][k]);
+    L.rb = longest;
     L.nslots = (size_t)L.nstrips * L.nchunks;
     L.off_mpart = 0;
     L.off_gpart = L.off_mpart + align_up(sizeof(double) * kNM * L.nslots, 256);
@@ -1024,6 +1116,37 @@ extern "C" int hicgat_pairloss_set_tuning(int rows_per_cta, int variant) {
     return HICGAT_OK;
 }
 
+extern "C" int hicgat_pairloss_set_schedule(int tail_depth, int tail_min_rows) {
+    if (tail_depth < -1 || tail_depth > 8 || tail_min_rows < 64 || tail_min_rows > 4096) {
+        set_error("hicgat_pairloss_set_schedule: tail_depth must be -1 (default) or 0..8, tail_min_rows 64..4096");
+        return HICGAT_ERR_INVALID;
+    }
+    g_tail_depth = tail_depth;
+    g_tail_min_rows = tail_min_rows;
+    return HICGAT_OK;
+}
+
+extern "C" int hicgat_pairloss_describe_schedule(int64_t n, int64_t r0, int64_t r1, int32_t* out, int32_t capacity) {
+    if (n <= 0 || r0 < 0 || r1 < r0 || r1 > n || !out || capacity < 4) {
+        set_error("hicgat_pairloss_describe_schedule: bad arguments");
+        return HICGAT_ERR_INVALID;
+    }
+    const Layout L = make_layout(n, r0, r1, g_variant);
+    const int need = 4 + (L.sch.count[0] + 1) + (L.sch.count[1] + 1);
+    if (capacity < need) {
+        set_error("hicgat_pairloss_describe_schedule: capacity %d < %d", (int)capacity, need);
+        return HICGAT_ERR_WORKSPACE;
+    }
+    int k = 0;
+    out[k++] = L.nstrips;
+    out[k++] = L.stagger;
+    out[k++] = L.sch.count[0];
+    out[k++] = L.sch.count[1];
+    for (int par = 0; par < 2; ++par)
+        for (int c = 0; c <= L.sch.count[par]; ++c) out[k++] = L.sch.bounds[par][c];
+    return k;
+}
+
 extern "C" size_t hicgat_pairloss_workspace_bytes(int64_t n, int64_t r0, int64_t r1) {
     if (n <= 0 || r0 < 0 || r1 < r0 || r1 > n) return 0;
     // for the CURRENT tuning (re-query after set_tuning); covers either variant
@@ -1065,7 +1188,7 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     }
     Params P;
     P.coords = coords; P.target = target; P.pitch = pitch;
-    P.n = (int)n; P.r0 = (int)r0; P.r1 = (int)r1; P.rb = L.rb; P.nstrips = L.nstrips; P.nchunks = L.nchunks; P.stagger = L.stagger;
+    P.n = (int)n; P.r0 = (int)r0; P.r1 = (int)r1; P.rb = L.rb; P.nstrips = L.nstrips; P.nchunks = L.nchunks; P.stagger = L.stagger; P.sch = L.sch;
     P.fill = 0.f;
     P.c_mse = c_mse; P.c_l1 = c_l1; P.moments = moments; P.grad = grad; P.grad64 = grad64;
     P.mpart = reinterpret_cast<double*>(ws + L.off_mpart);
@@ -1174,7 +1297,7 @@ static int pairloss_sparse_impl(const float* coords, const int32_t* rowptr, cons
     }
     Params P;
     P.coords = coords; P.target = nullptr; P.pitch = 0;
-    P.n = (int)n; P.r0 = (int)r0; P.r1 = (int)r1; P.rb = L.dense.rb; P.nstrips = L.dense.nstrips; P.nchunks = L.dense.nchunks; P.stagger = L.dense.stagger;
+    P.n = (int)n; P.r0 = (int)r0; P.r1 = (int)r1; P.rb = L.dense.rb; P.nstrips = L.dense.nstrips; P.nchunks = L.dense.nchunks; P.stagger = L.dense.stagger; P.sch = L.dense.sch;
     P.fill = fill;
     P.c_mse = c_mse; P.c_l1 = c_l1; P.moments = moments; P.grad = grad; P.grad64 = grad64;
     P.mpart = reinterpret_cast<double*>(ws + L.dense.off_mpart);

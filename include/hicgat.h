@@ -101,6 +101,15 @@ HICGAT_API int hicgat_pairloss_fwd_bwd_packed(const float* coords, const float* 
  * 0 = TMA tile ring (cp.async.bulk.tensor + mbarrier, default), 1 = per-lane streaming loads,
  * 2 = TMA tile ring without the half-chunk stagger of the second CTA slot (A/B only). */
 HICGAT_API int hicgat_pairloss_set_tuning(int rows_per_cta, int variant);
+/* Tuning hook (bench/tests): shape of the row-chunk schedule.  Every column strip is cut into chunks of
+ * about rows_per_cta rows followed by `tail_depth` chunks that halve each time (down to tail_min_rows), so
+ * that the CTAs dispatched last are short and the CTA slots run dry together.  tail_depth -1 = library
+ * default, 0 = equal chunks. */
+HICGAT_API int hicgat_pairloss_set_schedule(int tail_depth, int tail_min_rows);
+/* Introspection (tests): the row-chunk schedule the CURRENT tuning gives rows [r0, r1) of an n-locus map.
+ * out = [nstrips, stagger, count0, count1, bounds0[0..count0], bounds1[0..count1]] (row offsets from r0; table 1
+ * is used by the staggered strips).  Returns the number of ints written or a negative error code. */
+HICGAT_API int hicgat_pairloss_describe_schedule(int64_t n, int64_t r0, int64_t r1, int32_t* out, int32_t capacity);
 
 /* ------------------------------------------------------------------------------------
  * (next row f-4) The same loss against an IMPLICIT target for sparse maps: after cont2dist every

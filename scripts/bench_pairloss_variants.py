@@ -27,14 +27,17 @@ def rel(a, b):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variants", default="0", help="comma list of variant[:rows_per_cta], e.g. 0,0:512,0:1024,1")
+    ap.add_argument("--variants", default="0", help="comma list of variant[:rows_per_cta[:tail_depth[:tail_min_rows]]], e.g. 0,0:512,0:1024:2:256,1")
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--mode", default="mse_moments")
     ap.add_argument("--sizes", default="49850,9970,2493")
     ap.add_argument("--worlds", default="1,2,4,8,16")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
-    variants = [(int(v.split(":")[0]), int(v.split(":")[1]) if ":" in v else 0) for v in args.variants.split(",")]
+    variants = []
+    for v in args.variants.split(","):
+        f = [int(x) for x in v.split(":")] + [0, -1, 256]
+        variants.append((f[0], f[1] if len(v.split(":")) > 1 else 0, f[2] if len(v.split(":")) > 2 else -1, f[3] if len(v.split(":")) > 3 else 256))
     mode = ops._MODES[args.mode]
     dev = torch.device("cuda", 0)
     rows_out = []
@@ -49,8 +52,9 @@ def main():
                 continue
             tgt = ops.WishTarget(data[:rows], n, 0, rows)
             ref = None
-            for v, rb in variants:
+            for v, rb, td, tm in variants:
                 N.set_pairloss_tuning(rb, v)
+                N.set_pairloss_schedule(td, tm)
                 for _ in range(10):
                     m, g = ops.pairloss_raw(coords, tgt, mode, c_mse, c_l1)
                 ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.iters)]
@@ -63,7 +67,7 @@ def main():
                 ts = sorted(a.elapsed_time(b) for a, b in ev)
                 mean, lo, med = sum(ts) / len(ts), ts[0], ts[len(ts) // 2]
                 gbs = rows * n * 4 / (med * 1e-3) / 1e9
-                rec = {"n": n, "rows": rows, "variant": v, "rb": rb, "ms_mean": mean, "ms_med": med, "ms_min": lo, "gbs_med": gbs}
+                rec = {"n": n, "rows": rows, "variant": v, "rb": rb, "tail": [td, tm], "ms_mean": mean, "ms_med": med, "ms_min": lo, "gbs_med": gbs}
                 if ref is None:
                     ref = (m.clone(), g.clone())
                 else:
@@ -71,6 +75,7 @@ def main():
                 rows_out.append(rec)
                 print(json.dumps(rec), flush=True)
             N.set_pairloss_tuning(0, 0)
+            N.set_pairloss_schedule(-1, 256)
         del data
         torch.cuda.empty_cache()
     if args.out:
