@@ -595,7 +595,7 @@ def run_native(args):
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", "r1_pairloss_traffic.json"))).get(f"{nloc}x{n}")
             if t and args.variant == 0:
-                traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"])
+                traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"] + t.get("combine_dram_bytes_read", 0))
         except Exception:
             pass
         line = {
@@ -606,7 +606,8 @@ def run_native(args):
                        "timed_attempts": attempts, "l2": f"no flush: each step streams {target_bytes / 1e6:.0f} MB of target per rank (L2 is 126 MB)",
                        "setup_s": round(t_setup, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "pairloss_tma_kernel" if args.variant == 0 else "pairloss_ldg_kernel", "kernel_ms": kern_ms, "algorithmic_bytes": nloc * n * 4.0, "peak_source": peak_src,
+                         "kernel": ("pairloss_tma_kernel" if args.variant == 0 else "pairloss_ldg_kernel") + " + pairloss_combine_kernel", "kernel_ms": kern_ms,
+                         "note": "kernel_ms = CUDA events around the two launches of one loss evaluation; peak is a COPY bandwidth (half reads, half writes): a read-only stream can exceed it slightly", "algorithmic_bytes": nloc * n * 4.0, "peak_source": peak_src,
                          "frac_of_spec_8000": achieved / 8000.0,
                          "copy_gbs_this_run": copy_gbs, "frac_of_copy_this_run": (achieved / copy_gbs) if copy_gbs else None},
             "cpu_baseline": cpu,

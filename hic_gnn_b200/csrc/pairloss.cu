@@ -388,15 +388,15 @@ __device__ __forceinline__ void publish_cta(const Params& P, CombineSmem& S, int
 
 // Cross-CTA sums in a FIXED order (bit-reproducible).  Blocks 0 .. nstrips-1: the strip's gradient =
 // its row-chunk partials added in chunk order in f64, scaled, rounded once to f32.  Block nstrips: the
-// moments = every CTA's f64 partial, thread t taking slots t, t+256, ... (slots of chunks a strip does
+// moments = every CTA's f64 partial, thread t taking slots t, t+512, ... (slots of chunks a strip does
 // not have are skipped), then lanes, then warps.
-constexpr int kCombineThreads = 256;
+constexpr int kCombineThreads = 512;
 // `npass` = 2 under programmatic dependent launch: the blocks become resident while the producer's last
 // wave is still streaming, and the producer has pushed everything else -- including this kernel's
-// instructions -- out of L2 (400 MB+ go through 126 MB), so the first execution of the body after the
-// wait would pay one DRAM round trip per instruction-cache line (measured: 3-8 us for ~1 us of work).
-// Pass 0 therefore runs the SAME code on whatever the buffers hold, stores nothing, and leaves the
-// instruction cache, the TLB entries and the parameter loads warm; pass 1 follows the wait.
+// instructions -- out of L2 (400 MB+ go through 126 MB).  Pass 0 therefore runs the SAME code on whatever
+// the buffers hold, stores nothing, and leaves the instruction cache, the TLB entries and the parameter
+// loads warm; pass 1 follows the wait (moment block of a 1 560-partial grid: 8.6 -> 5.4 us after the wait,
+// %globaltimer stamps; the gradient blocks did not change).
 __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const Params P, const float scale, const int want_grad, const int npass) {
     const int tid = threadIdx.x;
     __shared__ double s_m[kCombineThreads / 32][kNM];
@@ -417,37 +417,25 @@ __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const
             if (!want_grad) return;
             const int strip = blockIdx.x;
             const int count = P.sch.count[strip_parity(P, strip)];
-            // elements tid and tid + 256 of the strip's 384, 8 chunks per round: 16 independent loads in flight,
-            // added in chunk order (out-of-range terms are +0.0, which leaves the sum unchanged)
-            const int i0 = tid, i1 = tid + kCombineThreads;
-            const bool has1 = i1 < kCols * 3;
-            const float* src0 = P.gpart + (size_t)strip * (kCols * 3) + i0;
-            const float* src1 = src0 + (has1 ? kCombineThreads : 0);
-            const size_t stride = (size_t)P.nstrips * (kCols * 3);
-            double s0 = 0.0, s1 = 0.0;
-            for (int c = 0; c < count; c += 8) {
-                float v0[8], v1[8];
+            // one element of the strip's 384 per thread, 8 chunks per round: 8 independent loads in flight, added
+            // in chunk order (out-of-range terms are +0.0, which leaves the sum unchanged)
+            if (tid < kCols * 3) {
+                const float* src = P.gpart + (size_t)strip * (kCols * 3) + tid;
+                const size_t stride = (size_t)P.nstrips * (kCols * 3);
+                double sum = 0.0;
+                for (int c = 0; c < count; c += 8) {
+                    float v[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const bool in = c + k < count;
-                    v0[k] = in ? __ldcg(src0 + (size_t)(c + k) * stride) : 0.f;
-                    v1[k] = (in && has1) ? __ldcg(src1 + (size_t)(c + k) * stride) : 0.f;
+                    for (int k = 0; k < 8; ++k) v[k] = c + k < count ? __ldcg(src + (size_t)(c + k) * stride) : 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) sum += (double)v[k];
                 }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    s0 += (double)v0[k];
-                    s1 += (double)v1[k];
+                if (live && strip * kCols + tid / 3 < P.n) {
+                    const double val = sum * (double)scale;
+                    if (P.grad) P.grad[(size_t)strip * kCols * 3 + tid] = (float)val;
+                    if (P.grad64) P.grad64[(size_t)strip * kCols * 3 + tid] = (double)(float)val;
                 }
             }
-            auto put = [&](int e, double s) {
-                if (live && strip * kCols + e / 3 < P.n) {
-                    const double v = s * (double)scale;
-                    if (P.grad) P.grad[(size_t)strip * kCols * 3 + e] = (float)v;
-                    if (P.grad64) P.grad64[(size_t)strip * kCols * 3 + e] = (double)(float)v;
-                }
-            };
-            put(i0, s0);
-            if (has1) put(i1, s1);
         } else {
             double m[kNM];
 #pragma unroll

@@ -70,6 +70,9 @@ HICGAT_API uint64_t hicgat_launch_count(void);
  *   [6] sum_{i<j} d*t  [7] sum_{i<j} (d-t)^2
  * grad [n,3] f32: this rank's contribution to dLoss/dcoords for ALL n loci (all-reduce when
  * sharded).  Results are bit-reproducible run to run (fixed-order reductions, no float atomics).
+ * One call enqueues TWO kernels: the streaming kernel (per-CTA partials into `workspace`) and a small
+ * combine kernel launched behind it with programmatic dependent launch (set HICGAT_NO_PDL=1 in the
+ * environment for a plain stream-ordered launch); both are capturable in a CUDA graph.
  * ---------------------------------------------------------------------------------- */
 #define HICGAT_PAIR_GRAD_MSE 1u
 #define HICGAT_PAIR_GRAD_L1 2u
@@ -79,9 +82,10 @@ HICGAT_API uint64_t hicgat_launch_count(void);
  * as 0).  sum t and sum t^2 are constants of the target: take them ONCE from a
  * HICGAT_PAIR_MOMENTS launch.  Implied by HICGAT_PAIR_MOMENTS. */
 #define HICGAT_PAIR_MOMENTS_D 8u
-/* The ticket counters at the start of `workspace` (4*(ceil(n/128)+1) bytes) are known to be zero:
- * skips the reset memset.  Every successful call leaves them zeroed, so a caller that zero-fills
- * a workspace once and uses it for nothing else may set this bit on every call. */
+/* Accepted and ignored by hicgat_pairloss_fwd_bwd since the cross-CTA sums moved into their own kernel (the
+ * dense-target workspace holds no state between calls).  hicgat_pairloss_sparse_fwd_bwd still keeps ONE
+ * ticket counter for its CSR correction pass: with this bit the caller promises it is zero (every
+ * successful call leaves it zeroed) and the reset memset is skipped. */
 #define HICGAT_PAIR_WS_CLEAN 16u
 #define HICGAT_PAIR_NMOM 8
 
