@@ -16,7 +16,7 @@ from torch import nn
 from torch.nn import LayerNorm, Linear
 
 from .layers import GATConv, SAGEConv
-from .ops import pairdist
+from .ops import ln_relu_add, pairdist
 
 
 class _CoordNet(nn.Module):
@@ -59,12 +59,14 @@ class GATNetSelectiveResidualsUpdated(_CoordNet):
         self.dense3 = Linear(64, 3)
 
     def get_model(self, x, edge_index, edge_weight=None):  # models.py:664-691
+        # F.relu(norm(dense(x))) + x_initial: LayerNorm + ReLU + residual add run as ONE kernel per direction
+        # (ops.ln_relu_add); the Linear layers stay cuBLAS
         x = F.relu(self.conv(x, edge_index, edge_weight))
         x_initial = self.align_densea(x)
-        x = F.relu(self.norm_a(self.densea(x))) + x_initial
+        x = ln_relu_add(self.densea(x), self.norm_a, x_initial)
         x_initial = self.align_dense1(x)
-        x = F.relu(self.norm1(self.dense1(x))) + x_initial
-        x = F.relu(self.norm2(self.dense2(x)))
+        x = ln_relu_add(self.dense1(x), self.norm1, x_initial)
+        x = ln_relu_add(self.dense2(x), self.norm2)
         return self.dense3(x)
 
 

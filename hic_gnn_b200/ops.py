@@ -336,6 +336,52 @@ def csr_from_dense(adj: torch.Tensor, with_self_loops: bool = False):
     return rowptr, col, val
 
 
+# ------------------------------------------------------------------------------ MLP-head glue
+class _LnReluAddFn(torch.autograd.Function):
+    """``relu(layer_norm(x)) [+ residual]`` in one kernel each way (``hicgat_ln_relu_add_fwd/bwd``)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, eps):
+        _cuda(x, residual, weight, bias)
+        if x.dtype != torch.float32 or x.dim() != 2:
+            raise RuntimeError("ln_relu_add expects a float32 [n, c] tensor")
+        x = x.contiguous()
+        res = residual.contiguous() if residual is not None else None
+        if res is not None and res.shape != x.shape:
+            raise RuntimeError("ln_relu_add: residual must have the shape of x")
+        n, c = x.shape
+        w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        y = torch.empty_like(x)
+        mean = torch.empty(n, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+        N.check(N.lib().hicgat_ln_relu_add_fwd(x.data_ptr(), _ptr(res), w.data_ptr(), b.data_ptr(), float(eps), n, c, y.data_ptr(), mean.data_ptr(),
+                                               rstd.data_ptr(), _stream()), "hicgat_ln_relu_add_fwd")
+        ctx.save_for_backward(x, mean, rstd, w, b)
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mean, rstd, w, b = ctx.saved_tensors
+        gy = gy.contiguous()
+        n, c = x.shape
+        dx = torch.empty_like(x)
+        dgamma = torch.empty_like(w)
+        dbeta = torch.empty_like(b)
+        ws = torch.empty(N.lib().hicgat_ln_relu_add_bwd_workspace_bytes(n, c), dtype=torch.uint8, device=x.device)
+        N.check(N.lib().hicgat_ln_relu_add_bwd(gy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), w.data_ptr(), b.data_ptr(), n, c, dx.data_ptr(),
+                                               dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "hicgat_ln_relu_add_bwd")
+        return dx, (gy if ctx.has_res else None), dgamma, dbeta, None
+
+
+def ln_relu_add(x: torch.Tensor, norm: torch.nn.LayerNorm, residual: torch.Tensor | None = None) -> torch.Tensor:
+    """``F.relu(norm(x)) + residual`` of the GAT net's MLP head (models.py:670-690) as one fused kernel per
+    direction; ``norm`` stays an ``nn.LayerNorm`` module (same parameters / ``state_dict`` keys)."""
+    if tuple(norm.normalized_shape) != (x.shape[-1],) or norm.weight is None or norm.bias is None:
+        raise RuntimeError("ln_relu_add: LayerNorm over the last dimension with affine parameters expected")
+    return _LnReluAddFn.apply(x, residual, norm.weight, norm.bias, norm.eps)
+
+
 # ------------------------------------------------------------------------------ host-buffer entry
 class HostPairLoss:
     """Pairwise loss for a target that lives in (pinned) HOST memory: the row blocks are

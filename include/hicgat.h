@@ -157,6 +157,21 @@ HICGAT_API int hicgat_pairdist_bwd(const float* coords, int64_t n, const float* 
                         float* grad_coords, hicgat_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Elementwise glue of the GAT net's MLP head between its (cuBLAS) Linear layers:
+ *   y = relu(LayerNorm_c(x; gamma, beta, eps)) + residual        (residual may be NULL)
+ * Replaces F.relu(self.norm_a(self.densea(x))) + x_initial, ...norm1..., F.relu(self.norm2(...))
+ * (models.py:670-690) and their autograd backward.  x, y, residual, grad_y, dx: [n, c] f32 row-major, c in
+ * {32, 64, 128, 256, 512}; mean / rstd: [n] f32 saved for the backward (biased variance, like
+ * torch.nn.LayerNorm).  Backward: dx [n, c], dgamma [c], dbeta [c] (the residual's gradient is grad_y itself).
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API int hicgat_ln_relu_add_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float eps,
+                           int64_t n, int32_t c, float* y, float* mean, float* rstd, hicgat_stream_t stream);
+HICGAT_API size_t hicgat_ln_relu_add_bwd_workspace_bytes(int64_t n, int32_t c);
+HICGAT_API int hicgat_ln_relu_add_bwd(const float* grad_y, const float* x, const float* mean, const float* rstd, const float* gamma,
+                           const float* beta, int64_t n, int32_t c, float* dx, float* dgamma, float* dbeta, void* workspace,
+                           size_t workspace_bytes, hicgat_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Wish-distance builder.  Replaces utils.cont2dist (utils.py:75-80) plus the per-iteration
  * truth.float() cast (HiC-GNN_main.py:127).
  *   pass 1: max over finite off-diagonal (1/a)^factor     -> max_out (f64 scalar, device)
