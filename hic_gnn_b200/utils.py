@@ -1,5 +1,7 @@
 """``utils.py`` of the reference, GPU edition: ``load_input`` (utils.py:29-73) and
-``cont2dist`` (utils.py:75-80) with the same names, arguments and return fields.
+``cont2dist`` (utils.py:75-80) with the same names, arguments and return fields, plus the helpers
+either side of the hot path: ``convert_to_matrix`` (utils.py:10-26), ``domain_alignment`` /
+``domain_alignment_filtered`` (utils.py:83-146) and ``WritePDB`` (utils.py:149-192).
 """
 from __future__ import annotations
 
@@ -81,3 +83,64 @@ def sparse_wish_target(data: Data, factor: float) -> ops.SparseWishTarget:
     stored pairs of ``data.edge_index``; every other pair is 1.0, the diagonal 0.  Same loss, no N x N
     array."""
     return ops.SparseWishTarget.from_graph(data.edge_index, data.y, factor)
+
+
+# ------------------------------------------------------------------------------ generalisation helpers (rows f-3 / f-4)
+def _bin_ids(lst, device):
+    a = torch.as_tensor(np.asarray(lst) if not torch.is_tensor(lst) else lst, dtype=torch.float64).to(device)
+    idx = torch.unique(a[:, 0]).long()                    # np.unique(list[:, 0]).astype(int), utils.py:84,87
+    return idx, int((idx[1:] - idx[:-1]).min())           # utils.py:85,88
+
+
+def domain_alignment(list1, list2, embeddings1, embeddings2, device="cuda", _filtered: bool = False) -> torch.Tensor:
+    """``utils.domain_alignment`` (utils.py:83-108): orthogonal Procrustes fit of ``embeddings2`` (the map to
+    generalise to, contact list ``list2``) onto ``embeddings1`` (the map the network was trained on) over the bins
+    the two resolutions share, applied to all of ``embeddings2``.  Bin matching (``unique`` / ``isin``), the
+    cross-covariance GEMM, the SVD and the final product run on the GPU in f64 (library calls around device
+    memory: this is data preparation, not the hot path); returns a CUDA f64 tensor."""
+    e1 = torch.as_tensor(np.asarray(embeddings1) if not torch.is_tensor(embeddings1) else embeddings1).to(device=device, dtype=torch.float64)
+    e2 = torch.as_tensor(np.asarray(embeddings2) if not torch.is_tensor(embeddings2) else embeddings2).to(device=device, dtype=torch.float64)
+    idx1, diff1 = _bin_ids(list1, device)
+    idx2, diff2 = _bin_ids(list2, device)
+    bins = int(diff1 / (2 * diff2))                       # utils.py:90
+    a_rows, b_rows = [], []
+    for i in range(bins + 1):                             # utils.py:95-100
+        shifted = idx2 + i * diff2
+        aidx = torch.nonzero(torch.isin(shifted, idx1)).flatten()
+        bidx = torch.nonzero(torch.isin(idx1, shifted)).flatten()
+        if _filtered:                                     # utils.py:126-131
+            aidx, bidx = aidx[aidx < e2.shape[0]], bidx[bidx < e1.shape[0]]
+            if aidx.numel() == 0 or bidx.numel() == 0:
+                continue
+        elif (aidx.numel() and int(aidx.max()) >= e2.shape[0]) or (bidx.numel() and int(bidx.max()) >= e1.shape[0]):
+            # numpy raises here in the reference; checked on the host so that no device-side assert can fire
+            raise IndexError("domain_alignment: the contact lists name more bins than the embeddings have rows")
+        a_rows.append(aidx)
+        b_rows.append(bidx)
+    if not a_rows:
+        raise ValueError("No valid alignment indices found. Check your input data.")  # utils.py:135-136
+    a, b = e2[torch.cat(a_rows)], e1[torch.cat(b_rows)]
+    if a.shape != b.shape:
+        raise ValueError(f"shapes {tuple(a.shape)} and {tuple(b.shape)} of the matched embeddings differ")  # scipy raises alike
+    u, _, vh = torch.linalg.svd(a.t() @ b)                # scipy.linalg.orthogonal_procrustes: svd((B^T A)^T), R = U V^T
+    return e2 @ (u @ vh)                                  # utils.py:106
+
+
+def domain_alignment_filtered(list1, list2, embeddings1, embeddings2, device="cuda") -> torch.Tensor:
+    """``utils.domain_alignment_filtered`` (utils.py:111-146): same, with out-of-range rows dropped."""
+    return domain_alignment(list1, list2, embeddings1, embeddings2, device, _filtered=True)
+
+
+def WritePDB(positions, pdb_file, ctype="0"):
+    """``utils.WritePDB`` (utils.py:149-192): byte-identical output (one leading blank line, ``ATOM`` records with
+    ``%.3f`` coordinates in 8-wide fields, ``CONECT i i+1`` records -- including the dangling last one unless
+    ``ctype == "1"`` --, ``END`` without a newline).  Accepts a CUDA / CPU tensor or an array (one device->host copy)."""
+    pos = positions.detach().cpu().numpy() if torch.is_tensor(positions) else np.asarray(positions)
+    n = len(pos)
+    out = ["\n"]
+    out += ["ATOM  %5s   CA MET %-6s   %8s%8s%8s  0.20 10.00\n" % (i, "B%d" % i, "%.3f" % p[0], "%.3f" % p[1], "%.3f" % p[2]) for i, p in enumerate(pos, 1)]
+    last = n - 1 if ctype == "1" else n
+    out += ["CONECT%5s%5s\n" % (i, i + 1) for i in range(1, last + 1)]
+    out.append("END")
+    with open(pdb_file, "w") as f:
+        f.write("".join(out))

@@ -20,6 +20,9 @@ Parity pin status:
 * The MLP heads of ``Net`` / the GAT nets are pinned against the reference's own
   ``models.py`` forward (imported with the conv layer stubbed) and the shipped
   ``Outputs/GM12878_1mb_chr19_list_weights.pt`` key/shape layout.
+* ``domain_alignment`` (utils.py:83-146) and ``WritePDB`` (utils.py:149-192) are PINNED against the
+  reference's own outputs (``tests/golden/make_golden_io.py``), ``WritePDB`` additionally against the shipped
+  ``Outputs/*_structure.pdb`` bytes.
 * GATConv / SAGEConv aggregation / ``SparseTensor.to_symmetric`` / ``set_diag`` live in
   un-vendored third-party wheels (torch-geometric 1.7.2, torch-sparse 0.6.11,
   torch-scatter 2.0.8) that are absent here and that no reference test pins:
@@ -27,4 +30,4 @@ Parity pin status:
   ``oracle/conv.py``.
 """
 
-from . import graph, kr, wish, conv, models, loss, loop  # noqa: F401
+from . import graph, kr, wish, conv, models, loss, loop, align  # noqa: F401
