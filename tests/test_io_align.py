@@ -99,3 +99,82 @@ def test_gpu_domain_alignment_rejects_mismatched_bins(golden):
         utils.domain_alignment(arrays["1mb_list"], arrays["500kb_list"], np.zeros((3, 8)), np.zeros((114, 8)))
     with pytest.raises(ValueError):  # the filtered variant drops the out-of-range rows, then the two sides differ in length
         utils.domain_alignment_filtered(arrays["1mb_list"], arrays["500kb_list"], np.zeros((3, 8)), np.zeros((114, 8)))
+
+
+@pytest.mark.gpu
+def test_gpu_alignment_of_512d_embeddings_reaches_the_same_optimum(golden):
+    """The reference's real shape: 512-d embeddings, 113 matched bin pairs drawn from 58 trained rows => the
+    cross-covariance has rank <= 58 and the minimiser of ||A R - B|| is not unique (LAPACK and cuSOLVER pick different
+    null-space bases).  What IS determined: R is orthogonal and the residual is the minimum."""
+    from hic_gnn_b200 import utils
+    from oracle import align
+
+    arrays, _ = golden
+    l1, l2 = arrays["1mb_list"], arrays["500kb_list"]
+    rng = np.random.default_rng(5)
+    e1, e2 = rng.standard_normal((58, 512)), rng.standard_normal((114, 512))
+    a_rows, b_rows = align.matched_rows(l1, l2)
+    want = align.domain_alignment(l1, l2, e1, e2)
+    got = utils.domain_alignment(l1, l2, e1, e2).cpu().numpy()
+    res_want = np.linalg.norm(want[a_rows] - e1[b_rows])
+    res_got = np.linalg.norm(got[a_rows] - e1[b_rows])
+    assert abs(res_got - res_want) < 1e-9 * res_want
+    # an orthogonal map: all pairwise inner products of the rows are preserved whatever the null-space basis
+    assert np.abs(got @ got.T - e2 @ e2.T).max() < 1e-8
+
+
+@pytest.mark.gpu
+def test_generalisation_flow_matches_oracle(golden, tmp_path):
+    """BASELINE.json configs[1] (HiC_GAT_generalize_directly.py:312-365) from a shared state_dict and a shared aligned
+    embedding: 500 kb graph + GAT net forward + dSCC + PDB on the GPU against the oracle's CPU flow."""
+    from hic_gnn_b200 import metrics, models as gmodels, utils as gutils
+    from oracle import align, graph as ograph, loss as oloss, models as omodels, wish as owish
+
+    arrays, _ = golden
+    l1, l2 = arrays["1mb_list"], arrays["500kb_list"]
+    normed2 = arrays["500kb_kr_oracle"]
+    rng = np.random.default_rng(9)
+    e1 = 0.25 * rng.standard_normal((58, 512))
+    e2 = 0.25 * rng.standard_normal((normed2.shape[0], 512))
+    fit = align.domain_alignment(l1, l2, e1, e2)                     # shared: see the rank remark above
+    torch.manual_seed(42)
+    om = omodels.GATNetSelectiveResidualsUpdated()
+    om.eval()
+    odata = ograph.load_input(normed2.copy(), fit)
+    truth = owish.cont2dist(odata.y.clone(), 1.0)
+    with torch.no_grad():
+        ocoords = om.get_model(odata.x.float(), odata.edge_index)
+    want = oloss.dscc(ocoords, truth)
+
+    gm = gmodels.GATNetSelectiveResidualsUpdated().cuda()
+    gm.load_state_dict(om.state_dict())
+    gm.eval()
+    gdata = gutils.load_input(normed2.copy(), fit)
+    target = gutils.wish_target(gdata.y, 1.0)
+    with torch.no_grad():
+        gcoords = gm.get_model(gdata.x.float(), gdata.edge_index)
+    scale = float(ocoords.abs().max())
+    assert float((gcoords.cpu() - ocoords).abs().max()) < 1e-4 * scale
+    assert abs(metrics.dscc(gcoords, target) - want) < 1e-3           # north_star: final dSCC within 1e-3
+    p1, p2 = tmp_path / "g.pdb", tmp_path / "o.pdb"
+    gutils.WritePDB(gcoords * 100, str(p1))
+    p2.write_text(align.write_pdb((ocoords * 100).numpy()))
+    a, b = p1.read_text().splitlines(), p2.read_text().splitlines()
+    assert len(a) == len(b) and sum(x != y for x, y in zip(a, b)) <= len(a) // 20  # %.3f of values that agree to 1e-4 relative
+
+
+@pytest.mark.gpu
+def test_generalisation_example_runs_end_to_end(monkeypatch, tmp_path):
+    import importlib.util
+    import sys
+
+    root = os.path.dirname(HERE)
+    spec = importlib.util.spec_from_file_location("chr19_generalize", os.path.join(root, "examples", "chr19_generalize.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = tmp_path / "gen.pdb"
+    monkeypatch.setattr(sys, "argv", ["chr19_generalize.py", "--steps", "40", "--out", str(out)])
+    hist, coords, d1, d2 = mod.main()
+    assert len(hist) <= 40 and hist[-1] < hist[0] and coords.shape == (114, 3) and bool(torch.isfinite(coords).all())
+    assert -1.0 <= d1 <= 1.0 and -1.0 <= d2 <= 1.0
+    assert out.read_text().count("ATOM") == 114
