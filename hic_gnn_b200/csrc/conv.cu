@@ -380,6 +380,184 @@ __global__ void __launch_bounds__(256) gat_bwd_node_kernel(const int32_t* __rest
     }
 }
 
+// ------------------------------------------------------------------ GAT backward, ONE gather pass (default)
+// The split backward above gathers 2 KB per edge twice (xl_j per target row, g_i per source row): 2 x 51 GB
+// through L1/L2 at 50k loci.  Both can be had from the source side alone:
+//   * the softmax row term  sum_k a_ik da_ik = <g_i, out_i - bias>_head  needs no gather at all
+//     (gat_bwd_rowdot_kernel, one row-wise pass over g and the saved forward output);
+//   * for source row j and its neighbour i (entry k' = (j,i), transposed entry kt = perm[k'] = (i,j)) the
+//     gathered g_i serves BOTH the accumulation  dxl_j += a_ij g_i  and the logit gradient
+//     da_ij = <g_i, xl_j>_head (xl_j sits in this warp's registers), from which dz_ij follows on the lane that
+//     owns the entry.  d a_src[j] = sum_i dz_ij accumulates on the spot; dz_ij is stored at kt so that
+//     d a_dst[i] = sum_j dz_ij becomes a contiguous row sum (gat_bwd_dst_kernel, which also adds the
+//     d a_dst[i] att_r term to dxl_i).
+// Same summation orders as the split kernels except for the row term (a dot product of two rows instead of a
+// sum over the row's edges): ~1e-7 relative.
+template <int H, int Q>
+__global__ void __launch_bounds__(256) gat_bwd_rowdot_kernel(const float* __restrict__ gout, const float* __restrict__ out,
+                                                             const float* __restrict__ bias, int n, float* __restrict__ rowdot) {
+    constexpr int F = Q * 128, QH = Q / H;
+    const int i = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    float s[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) s[h] = 0.f;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const float4 g = ldg_f4(gout + (size_t)i * F + q * 128 + lane * 4);
+        float4 o = ldg_f4(out + (size_t)i * F + q * 128 + lane * 4);
+        const float4 b = ldg_f4(bias + q * 128 + lane * 4);
+        o.x -= b.x; o.y -= b.y; o.z -= b.z; o.w -= b.w;
+        s[q / QH] += dot4(g, o);
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const float t = warp_sum(s[h]);
+        if (lane == 0) rowdot[i * H + h] = t;
+    }
+}
+
+template <int H, int Q>
+__global__ void __launch_bounds__(256, 2) gat_bwd_fused_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                               const int32_t* __restrict__ perm, const float* __restrict__ xl,
+                                                               const float* __restrict__ a_src, const float* __restrict__ a_dst,
+                                                               const float* __restrict__ alpha, const float* __restrict__ rowdot,
+                                                               const float* __restrict__ gout, const float* __restrict__ att_l, float slope,
+                                                               int n, float* __restrict__ dz, float* __restrict__ d_a_src,
+                                                               float* __restrict__ dxl) {
+    constexpr int F = Q * 128, QH = Q / H;
+    const int jn = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (jn >= n) return;
+    const int rs = rowptr[jn], re = rowptr[jn + 1];
+    float4 x[Q], acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        x[q] = ldg_f4(xl + (size_t)jn * F + q * 128 + lane * 4);
+        acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float asrc[H], ssrc[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        asrc[h] = a_src[jn * H + h];
+        ssrc[h] = 0.f;
+    }
+    for (int base = rs; base < re; base += 32) {
+        const int k = base + lane;
+        int myi = 0, mykt = 0;
+        float mya[H], myda[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) mya[h] = myda[h] = 0.f;
+        if (k < re) {
+            myi = col[k];
+            mykt = perm[k];
+#pragma unroll
+            for (int h = 0; h < H; ++h) mya[h] = alpha[(size_t)mykt * H + h];
+        }
+        const int cnt = min(32, re - base);
+        for (int t = 0; t < cnt; t += 4) {
+            int ii[4];
+            float a[4][H];
+            float4 v[4][Q];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ii[u] = __shfl_sync(0xffffffffu, myi, (t + u) & 31);
+#pragma unroll
+                for (int h = 0; h < H; ++h) a[u][h] = __shfl_sync(0xffffffffu, mya[h], (t + u) & 31);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) v[u][q] = ldg_f4(gout + (size_t)ii[u] * F + q * 128 + lane * 4);
+                }
+            float part[4][H];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) part[u][h] = 0.f;
+                if (t + u < cnt) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        part[u][q / QH] += dot4(x[q], v[u][q]);
+                        fma4(acc[q], a[u][q / QH], v[u][q]);
+                    }
+                }
+            }
+            // transpose-reduce butterfly of the 4 x H partial dot products (see gat_bwd_edge_kernel)
+            const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+            const int e = lane - t;  // entry of this group owned by this lane (valid for 0 <= e < 4)
+            const int src = ((e >> 1) & 1) << 4 | (e & 1) << 3;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                float w0 = (up16 ? part[2][h] : part[0][h]) + __shfl_xor_sync(0xffffffffu, up16 ? part[0][h] : part[2][h], 16);
+                float w1 = (up16 ? part[3][h] : part[1][h]) + __shfl_xor_sync(0xffffffffu, up16 ? part[1][h] : part[3][h], 16);
+                float y = (up8 ? w1 : w0) + __shfl_xor_sync(0xffffffffu, up8 ? w0 : w1, 8);
+                y += __shfl_xor_sync(0xffffffffu, y, 4);
+                y += __shfl_xor_sync(0xffffffffu, y, 2);
+                y += __shfl_xor_sync(0xffffffffu, y, 1);
+                const float d = __shfl_sync(0xffffffffu, y, src & 31);
+                if (e >= 0 && e < 4) myda[h] = d;
+            }
+        }
+        if (k < re) {  // softmax + leaky-relu backward on the lane that owns the entry
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float de = mya[h] * (myda[h] - rowdot[myi * H + h]);
+                const float z = asrc[h] + a_dst[myi * H + h];
+                const float d = z > 0.f ? de : de * slope;
+                dz[(size_t)mykt * H + h] = d;
+                ssrc[h] += d;
+            }
+        }
+    }
+    float dsrc[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        dsrc[h] = warp_sum(ssrc[h]);
+        if (lane == 0) d_a_src[jn * H + h] = dsrc[h];
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const float4 al = ldg_f4(att_l + q * 128 + lane * 4);
+        float4 o = acc[q];
+        const float sc = dsrc[q / QH];
+        o.x += sc * al.x; o.y += sc * al.y; o.z += sc * al.z; o.w += sc * al.w;
+        *reinterpret_cast<float4*>(dxl + (size_t)jn * F + q * 128 + lane * 4) = o;
+    }
+}
+
+// d a_dst[i,h] = sum of the row's dz (contiguous), then dxl[i,:] += d a_dst[i,h] att_r
+template <int H, int Q>
+__global__ void __launch_bounds__(256) gat_bwd_dst_kernel(const int32_t* __restrict__ rowptr, const float* __restrict__ dz,
+                                                          const float* __restrict__ att_r, int n, float* __restrict__ d_a_dst,
+                                                          float* __restrict__ dxl) {
+    constexpr int F = Q * 128, QH = Q / H;
+    const int i = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int rs = rowptr[i], re = rowptr[i + 1];
+    float s[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) s[h] = 0.f;
+    for (int k = rs + lane; k < re; k += 32) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) s[h] += dz[(size_t)k * H + h];
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        s[h] = warp_sum(s[h]);
+        if (lane == 0) d_a_dst[i * H + h] = s[h];
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const float4 ar = ldg_f4(att_r + q * 128 + lane * 4);
+        float4* p = reinterpret_cast<float4*>(dxl + (size_t)i * F + q * 128 + lane * 4);
+        float4 o = *p;
+        const float d = s[q / QH];
+        o.x += d * ar.x; o.y += d * ar.y; o.z += d * ar.z; o.w += d * ar.w;
+        *p = o;
+    }
+}
+
 // ------------------------------------------------------------------ GAT backward, step 3 (parameter grads)
 // datt_l[c] = sum_j d_a_src[j,h(c)] xl[j,c] ; datt_r[c] = sum_j d_a_dst[j,h(c)] xl[j,c] ; dbias[c] = sum_i g[i,c]
 // stage A: kParamCtas CTAs stride over the rows (float4 per thread, two rows in flight) and keep their sums in
@@ -499,7 +677,7 @@ extern "C" int hicgat_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t
 
 namespace {
 struct BwdLayout {
-    size_t off_dz, off_dsrc, off_ddst, off_part, off_counter, total;
+    size_t off_dz, off_dsrc, off_ddst, off_rowdot, off_part, off_counter, total;
     int nchunks;
 };
 BwdLayout bwd_layout(int64_t n, int64_t nnz, int H, int C) {
@@ -510,7 +688,8 @@ BwdLayout bwd_layout(int64_t n, int64_t nnz, int H, int C) {
     L.off_dz = 256;
     L.off_dsrc = L.off_dz + align_up(sizeof(float) * (size_t)nnz * H, 256);
     L.off_ddst = L.off_dsrc + align_up(sizeof(float) * (size_t)n * H, 256);
-    L.off_part = L.off_ddst + align_up(sizeof(float) * (size_t)n * H, 256);
+    L.off_rowdot = L.off_ddst + align_up(sizeof(float) * (size_t)n * H, 256);
+    L.off_part = L.off_rowdot + align_up(sizeof(float) * (size_t)n * H, 256);
     L.total = L.off_part + sizeof(float) * 3 * F * (size_t)param_ctas(n);
     return L;
 }
@@ -551,6 +730,50 @@ extern "C" int hicgat_gat_bwd(const int32_t* rowptr, const int32_t* col, const i
     HICGAT_DISPATCH_HQ(heads, channels, CALL_NODE);
 #undef CALL_NODE
     HICGAT_CHECK_LAUNCH("gat_bwd_node_kernel");
+    const int nblk = param_ctas(n);
+    gat_bwd_param_kernel<<<nblk, 128, 0, stream>>>(xl, gout, dsrc, ddst, (int)n, heads, channels, part);
+    HICGAT_CHECK_LAUNCH("gat_bwd_param_kernel");
+    gat_bwd_param_reduce_kernel<<<(3 * heads * channels + 7) / 8, 256, 0, stream>>>(part, nblk, heads * channels, datt_l, datt_r, dbias);
+    HICGAT_CHECK_LAUNCH("gat_bwd_param_reduce_kernel");
+    return HICGAT_OK;
+}
+
+extern "C" int hicgat_gat_bwd_fused(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n, int64_t nnz, int heads,
+                                    int channels, const float* xl, const float* att_l, const float* att_r, const float* bias, float slope,
+                                    const float* a_src, const float* a_dst, const float* alpha, const float* out, const float* gout,
+                                    float* dxl, float* datt_l, float* datt_r, float* dbias, void* workspace, size_t workspace_bytes,
+                                    hicgat_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HICGAT_REQUIRE(rowptr && col && perm && xl && att_l && att_r && bias && a_src && a_dst && alpha && out && gout && dxl && datt_l && datt_r && dbias && workspace,
+                   "hicgat_gat_bwd_fused: null pointer");
+    HICGAT_REQUIRE(n > 0 && n < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "hicgat_gat_bwd_fused: bad n/nnz");
+    HICGAT_REQUIRE(supported(heads, channels), "hicgat_gat_bwd_fused: unsupported heads=%d channels=%d", heads, channels);
+    HICGAT_REQUIRE(aligned16(xl) && aligned16(gout) && aligned16(out) && aligned16(dxl) && aligned16(att_l) && aligned16(att_r) && aligned16(bias),
+                   "hicgat_gat_bwd_fused: 16-byte alignment required");
+    const BwdLayout L = bwd_layout(n, nnz, heads, channels);
+    if (workspace_bytes < L.total) {
+        set_error("hicgat_gat_bwd_fused: workspace %zu < required %zu", workspace_bytes, L.total);
+        return HICGAT_ERR_WORKSPACE;
+    }
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    float* dz = reinterpret_cast<float*>(ws + L.off_dz);
+    float* dsrc = reinterpret_cast<float*>(ws + L.off_dsrc);
+    float* ddst = reinterpret_cast<float*>(ws + L.off_ddst);
+    float* rowdot = reinterpret_cast<float*>(ws + L.off_rowdot);
+    float* part = reinterpret_cast<float*>(ws + L.off_part);
+    const unsigned grid = (unsigned)((n + kRowsPerCta - 1) / kRowsPerCta);
+#define CALL_ROWDOT(H, Q) gat_bwd_rowdot_kernel<H, Q><<<grid, 256, 0, stream>>>(gout, out, bias, (int)n, rowdot)
+    HICGAT_DISPATCH_HQ(heads, channels, CALL_ROWDOT);
+#undef CALL_ROWDOT
+    HICGAT_CHECK_LAUNCH("gat_bwd_rowdot_kernel");
+#define CALL_FUSED(H, Q) gat_bwd_fused_kernel<H, Q><<<grid, 256, 0, stream>>>(rowptr, col, perm, xl, a_src, a_dst, alpha, rowdot, gout, att_l, slope, (int)n, dz, dsrc, dxl)
+    HICGAT_DISPATCH_HQ(heads, channels, CALL_FUSED);
+#undef CALL_FUSED
+    HICGAT_CHECK_LAUNCH("gat_bwd_fused_kernel");
+#define CALL_DST(H, Q) gat_bwd_dst_kernel<H, Q><<<grid, 256, 0, stream>>>(rowptr, dz, att_r, (int)n, ddst, dxl)
+    HICGAT_DISPATCH_HQ(heads, channels, CALL_DST);
+#undef CALL_DST
+    HICGAT_CHECK_LAUNCH("gat_bwd_dst_kernel");
     const int nblk = param_ctas(n);
     gat_bwd_param_kernel<<<nblk, 128, 0, stream>>>(xl, gout, dsrc, ddst, (int)n, heads, channels, part);
     HICGAT_CHECK_LAUNCH("gat_bwd_param_kernel");

@@ -8,6 +8,7 @@ library GEMMs and not part of the rewritten subsystems.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 from torch import nn
@@ -71,6 +72,10 @@ class SAGEConv(nn.Module):
         return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels})"
 
 
+# CSR GAT backward: "fused" (one 2 KB-per-edge gather pass) or "split" (two passes); env HICGAT_GAT_BWD overrides
+GAT_BACKWARD = os.environ.get("HICGAT_GAT_BWD", "fused")
+
+
 class _GatWorkspace:
     _cache: dict = {}
 
@@ -108,13 +113,13 @@ class _GatAttend(torch.autograd.Function):
                                    a_src.data_ptr(), a_dst.data_ptr(), alpha.data_ptr(), out.data_ptr(), _stream()),
             "hicgat_gat_fwd",
         )
-        ctx.save_for_backward(xl, att_l_f, att_r_f, a_src, a_dst, alpha)
+        ctx.save_for_backward(xl, att_l_f, att_r_f, bias_f, a_src, a_dst, alpha, out)
         ctx.graph, ctx.hc, ctx.slope, ctx.att_shape = graph, (heads, channels), slope, att_l.shape
         return out
 
     @staticmethod
     def backward(ctx, g):
-        xl, att_l_f, att_r_f, a_src, a_dst, alpha = ctx.saved_tensors
+        xl, att_l_f, att_r_f, bias_f, a_src, a_dst, alpha, out = ctx.saved_tensors
         graph, (heads, channels) = ctx.graph, ctx.hc
         g = g.contiguous()
         r32, c32, perm = graph.with_self_loops()
@@ -122,12 +127,20 @@ class _GatAttend(torch.autograd.Function):
         dxl = torch.empty_like(xl)
         datt_l, datt_r, dbias = torch.empty_like(att_l_f), torch.empty_like(att_r_f), torch.empty(heads * channels, dtype=torch.float32, device=xl.device)
         ws = _GatWorkspace.get(xl.device, n, nnz, heads, channels)
-        N.check(
-            N.lib().hicgat_gat_bwd(r32.data_ptr(), c32.data_ptr(), perm.data_ptr(), n, nnz, heads, channels, xl.data_ptr(), att_l_f.data_ptr(), att_r_f.data_ptr(), ctx.slope,
-                                   a_src.data_ptr(), a_dst.data_ptr(), alpha.data_ptr(), g.data_ptr(), dxl.data_ptr(), datt_l.data_ptr(), datt_r.data_ptr(), dbias.data_ptr(),
-                                   ws.data_ptr(), ws.numel(), _stream()),
-            "hicgat_gat_bwd",
-        )
+        if GAT_BACKWARD == "fused":  # one gather pass (default); "split" = the two-pass kernels, kept for A/B and as a cross-check
+            N.check(
+                N.lib().hicgat_gat_bwd_fused(r32.data_ptr(), c32.data_ptr(), perm.data_ptr(), n, nnz, heads, channels, xl.data_ptr(), att_l_f.data_ptr(), att_r_f.data_ptr(),
+                                             bias_f.data_ptr(), ctx.slope, a_src.data_ptr(), a_dst.data_ptr(), alpha.data_ptr(), out.data_ptr(), g.data_ptr(), dxl.data_ptr(),
+                                             datt_l.data_ptr(), datt_r.data_ptr(), dbias.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                "hicgat_gat_bwd_fused",
+            )
+        else:
+            N.check(
+                N.lib().hicgat_gat_bwd(r32.data_ptr(), c32.data_ptr(), perm.data_ptr(), n, nnz, heads, channels, xl.data_ptr(), att_l_f.data_ptr(), att_r_f.data_ptr(), ctx.slope,
+                                       a_src.data_ptr(), a_dst.data_ptr(), alpha.data_ptr(), g.data_ptr(), dxl.data_ptr(), datt_l.data_ptr(), datt_r.data_ptr(), dbias.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), _stream()),
+                "hicgat_gat_bwd",
+            )
         return dxl, datt_l.view(ctx.att_shape), datt_r.view(ctx.att_shape), dbias, None, None, None, None
 
 

@@ -247,6 +247,16 @@ HICGAT_API int hicgat_gat_bwd(const int32_t* rowptr, const int32_t* col, const i
                    const float* alpha, const float* gout, float* dxl, float* datt_l,
                    float* datt_r, float* dbias, void* workspace, size_t workspace_bytes,
                    hicgat_stream_t stream);
+/* Same backward with ONE 2 KB-per-edge gather pass instead of two (default of the Python layer): additionally takes
+ * the forward output `out` [n,H*C] and `bias`, from which the softmax row term <g_i, out_i - bias> is formed without
+ * touching the edges; the per-edge logit gradient and the dxl accumulation then share the gather of g_i from the
+ * source side.  Same workspace as hicgat_gat_bwd. */
+HICGAT_API int hicgat_gat_bwd_fused(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t n,
+                         int64_t nnz, int heads, int channels, const float* xl, const float* att_l,
+                         const float* att_r, const float* bias, float slope, const float* a_src,
+                         const float* a_dst, const float* alpha, const float* out, const float* gout,
+                         float* dxl, float* datt_l, float* datt_r, float* dbias, void* workspace,
+                         size_t workspace_bytes, hicgat_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * (1d) Dense-tile path of the same GATConv for near-dense graphs (1 Mb / 100 kb maps): per head the

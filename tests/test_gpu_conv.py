@@ -95,6 +95,29 @@ def test_gat_forward_backward(n, density, dense, path):
         assert rel_err(a, b) < 2e-5, name
 
 
+@pytest.mark.parametrize("n,density", [(58, 1.0), (300, 0.2), (1000, 0.05), (3000, 0.3)])
+def test_gat_csr_backward_one_pass_matches_two_pass(monkeypatch, n, density):
+    """The default CSR backward (one gather pass from the source side, softmax row term from <g_i, out_i - bias>)
+    against the two-pass kernels it replaces, on the same forward: every gradient within 1e-5."""
+    from hic_gnn_b200 import layers as glayers
+
+    x, _, gdata, oc = _gat_case(n, density, min_kink_gap=0.0)  # both kernels form z = a_src[j] + a_dst[i] identically: no kink issue
+    gc = glayers.GATConv(512, 256, heads=2).cuda()
+    gc.path = "csr"
+    gc.load_state_dict(oc.state_dict())
+    with torch.no_grad():
+        gc.bias.copy_(0.1 * torch.randn(512))   # a non-zero bias exercises the (out - bias) term
+    w = torch.randn(n, 512, generator=torch.Generator().manual_seed(1)).cuda()
+    grads = {}
+    for mode in ("split", "fused"):
+        monkeypatch.setattr(glayers, "GAT_BACKWARD", mode)
+        xg = x.cuda().requires_grad_(True)
+        yg = gc(xg, gdata.edge_index)
+        grads[mode] = torch.autograd.grad((yg * w).sum(), [xg, gc.lin_l.weight, gc.att_l, gc.att_r, gc.bias])
+    for name, a, b in zip(["x", "W", "att_l", "att_r", "bias"], grads["fused"], grads["split"]):
+        assert rel_err(a, b) < TOL, name
+
+
 def test_gat_at_c4_size_paths_agree_and_forward_matches_oracle():
     """BASELINE.json config 4 size (9 970 loci, ~7 % density, 7 M edges): the CSR warp-per-row path and the
     dense-tile path must agree on output and every gradient, and the forward must match the oracle's
