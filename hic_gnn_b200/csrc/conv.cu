@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(256) gat_bwd_dst_kernel(const int32_t* __restr
 // registers; partials are stored TRANSPOSED, part[(k*F + c) * nblk + blk], so that stage B -- one warp per
 // output value, lanes striding the nblk partials, fixed order -- reads them coalesced.  Deterministic.
 constexpr int kParamRows = 64;   // kept for the workspace formula (upper bound of the partial count)
-constexpr int kParamCtas = 148 * 2;
+constexpr int kParamCtas = 148 * 8;  // 4 warps each: ~32 warps per SM keep enough 16-byte loads in flight for a 204 MB stream
 __global__ void __launch_bounds__(128) gat_bwd_param_kernel(const float* __restrict__ xl, const float* __restrict__ gout,
                                                             const float* __restrict__ d_a_src, const float* __restrict__ d_a_dst,
                                                             int n, int H, int C, float* __restrict__ part) {

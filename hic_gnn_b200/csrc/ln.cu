@@ -134,23 +134,26 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_relu_add_bwd_kernel(const fl
     }
 }
 
-// d gamma [C] | d beta [C] = per-CTA partials added in CTA order
-__global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __restrict__ part, int nblk, int c2, int C, float* __restrict__ dgamma,
-                                                              float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c2) return;
+// d gamma [C] | d beta [C]: 32 columns per block, 32 threads per column each adding the partials blk = ty, ty + 32, ...
+// in order, then the 32 sub-sums in order (fixed association => bit-reproducible)
+__global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* __restrict__ part, int nblk, int c2, int C, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta) {
+    __shared__ float s_sum[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float s = 0.f;
-    int b = 0;
-    for (; b + 8 <= nblk; b += 8) {
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = part[(size_t)(b + k) * c2 + c];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s += v[k];
+    if (c < c2) {
+        for (int b = ty; b < nblk; b += 32) s += part[(size_t)b * c2 + c];
     }
-    for (; b < nblk; ++b) s += part[(size_t)b * c2 + c];
-    if (c < C) dgamma[c] = s;
-    else dbeta[c - C] = s;
+    s_sum[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < c2) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += s_sum[k][tx];
+        if (c < C) dgamma[c] = t;
+        else dbeta[c - C] = t;
+    }
 }
 
 int bwd_blocks(int64_t n) {
@@ -206,7 +209,7 @@ extern "C" int hicgat_ln_relu_add_bwd(const float* grad_y, const float* x, const
     float* part = static_cast<float*>(workspace);
     HICGAT_LN_DISPATCH(c, (ln_relu_add_bwd_kernel<V><<<nblk, kLnWarps * 32, 0, stream>>>(grad_y, x, mean, rstd, gamma, beta, (int)n, dx, part)));
     HICGAT_CHECK_LAUNCH("ln_relu_add_bwd_kernel");
-    ln_param_reduce_kernel<<<(2 * c + 255) / 256, 256, 0, stream>>>(part, nblk, 2 * c, c, dgamma, dbeta);
+    ln_param_reduce_kernel<<<(2 * c + 31) / 32, 1024, 0, stream>>>(part, nblk, 2 * c, c, dgamma, dbeta);
     HICGAT_CHECK_LAUNCH("ln_param_reduce_kernel");
     return HICGAT_OK;
 }
