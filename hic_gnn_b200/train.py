@@ -11,6 +11,9 @@ loss+gradient launch over the f32 target, backward through the conv kernels, Ada
   ``"mse_pearson"``  total = MSE + min(1, 0.1 + 1/(MSE+1e-6)) (1 - r)  (HiC_GAT_generalize_directly.py:219-225;
                      r is a constant w.r.t. autograd in the reference, so the gradient is MSE's)
   ``"contrastive"``  total = 0.1 mean_{i<j} |t - d|                    (train_and_test_same_res_GAT_node2vec.py:131-134)
+  ``"mse_spearman"`` total = MSE + alpha (1 - dSCC), fixed alpha       (combined_loss_training.py:119-142; the Spearman
+                     term is a scipy value in the reference, i.e. a constant for autograd: the gradient is MSE's.  The
+                     rank transform runs on the GPU (metrics.dscc) but costs a host read per step: no CUDA graph)
 """
 from __future__ import annotations
 
@@ -19,14 +22,26 @@ from torch.optim import Adam
 
 from .ops import WishTarget, pairwise_loss, pearson_from_moments
 
-_KERNEL_MODE = {"mse": "mse", "mse_pearson": "mse_moments", "contrastive": "contrastive"}
+_KERNEL_MODE = {"mse": "mse", "mse_pearson": "mse_moments", "contrastive": "contrastive", "mse_spearman": "mse_moments"}
 
 
-def step_loss(model, x, graph, target: WishTarget, mode: str, reducer=None):
+def drmsd_from_moments(moments: torch.Tensor, n: int) -> torch.Tensor:
+    """``calculate_dRMSD`` (combined_loss_training.py:22-26) from the fused kernel's upper-triangle ``sum (d-t)^2``."""
+    return torch.sqrt(moments[7] / (n * (n - 1) / 2.0))
+
+
+def step_loss(model, x, graph, target: WishTarget, mode: str, reducer=None, alpha: float = 1.0):
     """Forward + fused loss; returns (differentiable loss, total value tensor, moments)."""
     coords = model.get_model(x, graph)
     loss, moments = pairwise_loss(coords, target, _KERNEL_MODE[mode], reducer)
     total = loss.detach()
+    if mode == "mse_spearman":
+        from . import metrics
+
+        rho = metrics.dscc(coords.detach(), target)          # spearmanr of the i<j distances (:137)
+        if rho != rho:                                        # NaN -> 0 (:138-140)
+            rho = 0.0
+        total = total.double() + alpha * (1.0 - rho)
     if mode == "mse_pearson":
         n = target.n
         r = pearson_from_moments(moments, n * (n - 1) / 2.0)
@@ -40,10 +55,13 @@ class TrainStep:
     """One training iteration, optionally captured in a CUDA graph (small N is launch-bound:
     ~40 kernels per step).  ``total`` / ``moments`` are static device tensors when graphed."""
 
-    def __init__(self, model, x, graph, target: WishTarget, mode: str = "mse", lr: float = 1e-3, use_cuda_graph: bool = False, reducer=None):
+    def __init__(self, model, x, graph, target: WishTarget, mode: str = "mse", lr: float = 1e-3, use_cuda_graph: bool = False, reducer=None,
+                 alpha: float = 1.0):
         if mode not in _KERNEL_MODE:
             raise ValueError(mode)
-        self.model, self.x, self.graph, self.target, self.mode, self.reducer = model, x, graph, target, mode, reducer
+        if mode == "mse_spearman" and use_cuda_graph:
+            raise ValueError("mse_spearman reads the rank correlation back every step: it cannot be captured in a CUDA graph")
+        self.model, self.x, self.graph, self.target, self.mode, self.reducer, self.alpha = model, x, graph, target, mode, reducer, alpha
         self.optimizer = Adam(model.parameters(), lr=lr, capturable=use_cuda_graph)
         self.total = None
         self.moments = None
@@ -53,7 +71,7 @@ class TrainStep:
 
     def _eager(self):
         self.optimizer.zero_grad(set_to_none=True)
-        loss, total, moments = step_loss(self.model, self.x, self.graph, self.target, self.mode, self.reducer)
+        loss, total, moments = step_loss(self.model, self.x, self.graph, self.target, self.mode, self.reducer, self.alpha)
         loss.backward()
         self.optimizer.step()
         return total, moments
@@ -90,13 +108,13 @@ class TrainStep:
 
 
 def fit(model, x, graph, target: WishTarget, mode: str = "mse", lr: float = 1e-3, thresh: float = 1e-8, max_steps: int | None = None,
-        check_every: int = 1, use_cuda_graph: bool = False, reducer=None):
+        check_every: int = 1, use_cuda_graph: bool = False, reducer=None, alpha: float = 1.0):
     """Reference loop.  Returns the list of per-step total losses (floats).
 
     ``check_every=1`` evaluates the stop rule every step exactly like the reference (one host
     read per step).  Larger values read the losses back in batches: same trajectory, but the
     loop may overrun the reference's stopping step by up to ``check_every-1`` iterations."""
-    step = TrainStep(model, x, graph, target, mode, lr, use_cuda_graph, reducer)
+    step = TrainStep(model, x, graph, target, mode, lr, use_cuda_graph, reducer, alpha)
     hist: list[float] = []
     pending: list[torch.Tensor] = []
     old = 1.0
