@@ -34,3 +34,28 @@ def test_native_arm_needs_cuda():
         return
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_committed_native_lines_carry_the_contract_keys():
+    """The B200 lines committed under profiles/ (what DESIGN.md quotes) have every key the driver / judge reads, a
+    roofline consistent with its own fields, a CPU baseline and an end-to-end number with real copies."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_bench_c*_n[0-9].json")))
+    assert len(files) >= 4
+    for f in files:
+        line = json.loads(open(f).read().strip().splitlines()[-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                    "config", "roofline", "e2e", "gpu_launches", "clocks"):
+            assert key in line, (f, key)
+        assert line["metric"] == "pairwise_loss_gpairs_per_s" and line["unit"] == "Gpairs/s" and line["higher_is_better"] is True
+        assert line["warmup"] >= 3 and line["gpu_launches"] > 0 and "workload" in line["config"]
+        r = line["roofline"]
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert abs(r["achieved"] - r["algorithmic_bytes"] / (r["kernel_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and line["e2e"]["value"] < line["value"]
+        bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
+        assert not bad, (f, bad)
+        if line["n_gpus"] == 1 and "c5" in os.path.basename(f):
+            cb = line["cpu_baseline"]
+            assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb
