@@ -230,6 +230,21 @@ class GATConv(nn.Module):
         with torch.no_grad():
             self.bias.zero_()
 
+    # torch-geometric >= 2.0 renamed the parameters (lin_src / lin_dst / att_src / att_dst, later a single `lin`);
+    # checkpoints written there load into the 1.7.2 names the reference uses
+    _PYG2_KEYS = {"lin_src.weight": "lin_l.weight", "lin_dst.weight": "lin_r.weight", "lin.weight": "lin_l.weight", "att_src": "att_l", "att_dst": "att_r"}
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        for new, old in self._PYG2_KEYS.items():
+            if prefix + new in state_dict:
+                state_dict.setdefault(prefix + old, state_dict.pop(prefix + new))
+        l, r = prefix + "lin_l.weight", prefix + "lin_r.weight"   # one shared projection under two names (lin_r is lin_l)
+        if l in state_dict and r not in state_dict:
+            state_dict[r] = state_dict[l]
+        elif r in state_dict and l not in state_dict:
+            state_dict[l] = state_dict[r]
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
     def forward(self, x, edge_index, edge_weight=None, size=None):
         graph = as_graph(edge_index, edge_weight, x.shape[0])
         xl = self.lin_l(x)
