@@ -160,7 +160,11 @@ def test_generalisation_flow_matches_oracle(golden, tmp_path):
     gutils.WritePDB(gcoords * 100, str(p1))
     p2.write_text(align.write_pdb((ocoords * 100).numpy()))
     a, b = p1.read_text().splitlines(), p2.read_text().splitlines()
-    assert len(a) == len(b) and sum(x != y for x, y in zip(a, b)) <= len(a) // 20  # %.3f of values that agree to 1e-4 relative
+    assert len(a) == len(b) and [x for x in a if not x.startswith("ATOM")] == [y for y in b if not y.startswith("ATOM")]
+    xa = np.array([[float(x[30:38]), float(x[38:46]), float(x[46:54])] for x in a if x.startswith("ATOM")])
+    xb = np.array([[float(y[30:38]), float(y[38:46]), float(y[46:54])] for y in b if y.startswith("ATOM")])
+    assert xa.shape == (normed2.shape[0], 3) and np.abs(xa - xb).max() <= 1e-4 * 100 * scale + 1.5e-3   # %.3f of values within 1e-4 relative
+    assert [x[:30] for x in a] == [y[:30] for y in b]                                                    # record names / serials / residue ids
 
 
 @pytest.mark.gpu
