@@ -20,7 +20,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libhicgat_sm100.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
+    "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
     "-cudart", "static",
 ]
@@ -56,7 +56,7 @@ def _build(lib: str, objdir: str, extra: list, verbose: bool) -> str:
     os.makedirs(objdir, exist_ok=True)
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"], *extra, "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

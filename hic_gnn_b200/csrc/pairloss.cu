@@ -27,6 +27,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -1062,11 +1063,15 @@ cudaError_t launch_combine(const Params& P, cudaStream_t stream) {
 template <uint32_t MODE>
 cudaError_t launch_mode(int variant, const CUtensorMap& map, const Params& P, dim3 grid, cudaStream_t stream) {
     if (variant == 0) {
-        static bool attr_set = false;  // opt in to > 48 KB dynamic shared memory once per instantiation
-        if (!attr_set) {
+        // opt in to > 48 KB dynamic shared memory: a per-DEVICE function attribute, set once per (instantiation, device)
+        static std::atomic<uint64_t> attr_set{0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const uint64_t bit = 1ull << (dev & 63);
+        if (dev >= 64 || !(attr_set.load(std::memory_order_relaxed) & bit)) {
             cudaError_t e = cudaFuncSetAttribute(pairloss_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
             if (e != cudaSuccess) return e;
-            attr_set = true;
+            attr_set.fetch_or(bit, std::memory_order_relaxed);
         }
         pairloss_tma_kernel<MODE><<<grid, kThreads, kTmaSmem, stream>>>(map, P);
     } else {

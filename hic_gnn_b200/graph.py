@@ -58,7 +58,8 @@ class CSRGraph:
     @classmethod
     def from_edge_index(cls, edge_index: torch.Tensor, edge_weight: torch.Tensor | None, n: int):
         """``forward(x, edge_index, edge_weight)`` with a ``[2,E]`` LongTensor: sort row-major
-        (what SparseTensor's constructor does); duplicates are kept as given."""
+        (what SparseTensor's constructor does).  The pattern must be symmetric and duplicate-free (what
+        ``load_input`` produces); that is checked when the conv layers derive their index arrays."""
         _cuda(edge_index)
         row, col = edge_index[0].long(), edge_index[1].long()
         if edge_weight is None:
@@ -98,6 +99,7 @@ class CSRGraph:
             N.check(N.lib().hicgat_csr_add_self_loops_i32(r32.data_ptr(), c32.data_ptr(), self.n, orow.data_ptr(), ocol.data_ptr(), _stream()), "hicgat_csr_add_self_loops_i32")
             perm = torch.empty(self.nnz + self.n, dtype=torch.int32, device=self.device)
             N.check(N.lib().hicgat_csr_transpose_perm(orow.data_ptr(), ocol.data_ptr(), self.n, perm.data_ptr(), _stream()), "hicgat_csr_transpose_perm")
+            _check_transpose_perm(perm, "CSRGraph.with_self_loops")
             return orow, ocol, perm
 
         return self._get("self_loops", build)
@@ -130,9 +132,24 @@ class CSRGraph:
             perm = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=self.device)
             N.check(N.lib().hicgat_csr_transpose_perm(r32.data_ptr(), c32.data_ptr(), self.n, perm.data_ptr(), _stream()), "hicgat_csr_transpose_perm")
             norm = norm[: self.nnz]
+            _check_transpose_perm(perm[: self.nnz], "CSRGraph.sage_weights")
             return norm, norm[perm[: self.nnz].long()].contiguous()
 
         return self._get("sage", build)
+
+
+def _check_transpose_perm(perm: torch.Tensor, what: str) -> None:
+    """The backward kernels index ``alpha[perm]`` / ``dz[perm]``: every stored entry (i, j) needs its
+    transposed entry (j, i) exactly once.  ``hicgat_csr_transpose_perm`` writes -1 where (j, i) is missing;
+    duplicates break the involution.  One host read at graph-build time (the build already syncs)."""
+    if perm.numel() == 0:
+        return
+    p = perm.long()
+    if bool((p < 0).any()):
+        raise RuntimeError(f"{what}: the edge pattern is not symmetric (an entry (i, j) has no (j, i)); "
+                           "the conv backward kernels need a symmetric pattern, as utils.load_input builds it")
+    if not bool((p[p] == torch.arange(p.numel(), device=p.device)).all()):
+        raise RuntimeError(f"{what}: the edge pattern holds duplicate entries; coalesce the edge list first")
 
 
 def as_graph(edge_index, edge_weight=None, n: int | None = None) -> CSRGraph:

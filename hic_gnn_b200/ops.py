@@ -42,11 +42,15 @@ class WishTarget:
     The layout the fused loss kernel streams (``truth.float()`` of HiC-GNN_main.py:127,
     stored once instead of re-cast every iteration)."""
 
-    def __init__(self, data: torch.Tensor, n: int, r0: int, r1: int):
+    def __init__(self, data: torch.Tensor, n: int, r0: int, r1: int, symmetric: bool | None = None):
         _cuda(data)
         assert data.dtype == torch.float32 and data.dim() == 2 and data.stride(1) == 1
         assert data.shape[0] == r1 - r0 and data.stride(0) % 4 == 0 and data.stride(0) >= n
         self.data, self.n, self.r0, self.r1 = data, n, r0, r1
+        # True: t_ij == t_ji verified (or promised by the builder) -> column-side gradient is complete;
+        # False: verified asymmetric -> the row-side term is added by a second pass (MSE modes);
+        # None: a row block built without sight of the full matrix: the caller's contract, as documented in hicgat.h
+        self.symmetric = symmetric
 
     @property
     def pitch(self) -> int:
@@ -57,19 +61,26 @@ class WishTarget:
         return (n + 3) // 4 * 4
 
     @classmethod
-    def empty(cls, n: int, r0: int = 0, r1: int | None = None, device="cuda"):
+    def empty(cls, n: int, r0: int = 0, r1: int | None = None, device="cuda", symmetric: bool | None = None):
         r1 = n if r1 is None else r1
         buf = torch.zeros(max(r1 - r0, 1), cls.pitch_for(n), dtype=torch.float32, device=device)
-        return cls(buf[: r1 - r0], n, r0, r1)
+        return cls(buf[: r1 - r0], n, r0, r1, symmetric)
 
     @classmethod
-    def from_dense(cls, truth: torch.Tensor, r0: int = 0, r1: int | None = None):
-        """Copy rows [r0,r1) of an N x N (f32/f64) CUDA matrix into the padded layout."""
+    def from_dense(cls, truth: torch.Tensor, r0: int = 0, r1: int | None = None, symmetric: bool | None = None):
+        """Copy rows [r0,r1) of an N x N (f32/f64) CUDA matrix into the padded layout.  ``truth`` is the FULL
+        matrix, so its symmetry (of rows [r0,r1) against columns [r0,r1)) is checked here, once, unless the
+        caller states it (the reference does not symmetrise ``y``: utils.py:29-35)."""
         _cuda(truth)
         n = truth.shape[0]
         r1 = n if r1 is None else r1
         out = cls.empty(n, r0, r1, truth.device)
         out.data[:, :n].copy_(truth[r0:r1])
+        if symmetric is None:
+            # judged on the f32 values the kernel will stream (an f64 matrix whose asymmetry vanishes in the cast is symmetric for the kernel)
+            ref = truth if truth.dtype == torch.float32 else (out.data if (r0 == 0 and r1 == n) else truth.float())
+            symmetric = asymmetry(ref, r0, r1) == 0.0
+        out.symmetric = bool(symmetric)
         return out
 
     def dense(self) -> torch.Tensor:
@@ -126,6 +137,20 @@ class SparseWishTarget:
         return self._tmom
 
 
+def asymmetry(mat: torch.Tensor, r0: int = 0, r1: int | None = None) -> float:
+    """``max |M_ij - M_ji|`` over rows [r0,r1) of a full row-major f32/f64 CUDA matrix (``hicgat_asymmetry_*``);
+    one host read -- a build-time check, never per step."""
+    _cuda(mat)
+    if mat.dim() != 2 or mat.stride(1) != 1 or mat.shape[0] > mat.shape[1] or mat.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("asymmetry expects a row-major float32/float64 CUDA matrix with at least as many columns as rows")
+    n = mat.shape[0]
+    r1 = n if r1 is None else r1
+    out = torch.empty(1, dtype=torch.float64, device=mat.device)
+    fn = N.lib().hicgat_asymmetry_f32 if mat.dtype == torch.float32 else N.lib().hicgat_asymmetry_f64
+    N.check(fn(mat.data_ptr(), mat.stride(0), n, r0, r1, out.data_ptr(), _stream()), "hicgat_asymmetry")
+    return float(out)
+
+
 # ------------------------------------------------------------------------------ pair loss
 class _PairWorkspace:
     """Per (device, n, row block) scratch for the cross-CTA reductions, re-sized when the kernel
@@ -175,11 +200,19 @@ def pairloss_raw(coords: torch.Tensor, target: WishTarget, mode: int, c_mse: flo
     if grad is None and (mode & 3):
         grad = torch.empty(n, 3, dtype=torch.float32, device=coords.device)
     ws = _PairWorkspace.get(coords.device, n, target.r0, target.r1)
+    asym = target.symmetric is False and (mode & 3)
+    if asym and (mode & N.PAIR_GRAD_L1):
+        raise NotImplementedError("the contrastive (L1, i<j) gradient needs a symmetric target: t_ij != t_ji found when the target was built "
+                                  "(symmetrise it, e.g. (T + T.T)/2 or triu(T) + triu(T, 1).T, whichever the experiment means)")
     rc = N.lib().hicgat_pairloss_fwd_bwd(
-        coords.data_ptr(), target.data.data_ptr(), target.pitch, n, target.r0, target.r1, mode | N.PAIR_WS_CLEAN, c_mse, c_l1,
+        coords.data_ptr(), target.data.data_ptr(), target.pitch, n, target.r0, target.r1, mode | N.PAIR_WS_CLEAN, 0.5 * c_mse if asym else c_mse, c_l1,
         moments.data_ptr(), _ptr(grad), ws.data_ptr(), ws.numel(), _stream(),
     )
     N.check(rc, "hicgat_pairloss_fwd_bwd")
+    if asym:  # autograd of MSELoss(cdist(x), T) for T != T^T: column-side and row-side terms, (2/N^2) each
+        rc = N.lib().hicgat_pairloss_rowside_add(coords.data_ptr(), target.data.data_ptr(), target.pitch, n, target.r0, target.r1, 0.5 * c_mse,
+                                                 grad.data_ptr(), _stream())
+        N.check(rc, "hicgat_pairloss_rowside_add")
     return moments, grad
 
 
@@ -284,11 +317,14 @@ def pairdist(coords: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------ builders
-def cont2dist(adj: torch.Tensor, factor: float, want_f64: bool = True, want_f32: bool = False, r0: int = 0, r1: int | None = None, max_reduce=None):
+def cont2dist(adj: torch.Tensor, factor: float, want_f64: bool = True, want_f32: bool = False, r0: int = 0, r1: int | None = None, max_reduce=None,
+              symmetric: bool | None = None):
     """``utils.cont2dist`` (utils.py:75-80) on the GPU.  ``adj``: f64 CUDA rows [r0,r1) x n.
 
     Returns ``(f64 matrix or None, WishTarget or None)``.  ``max_reduce`` (sharded builds) is
-    called on the device scalar between the two passes (an all-reduce(max))."""
+    called on the device scalar between the two passes (an all-reduce(max)).  ``symmetric``: what the caller
+    knows about the contact matrix (the wish distance is elementwise, so it inherits the symmetry); a full
+    matrix (r0 = 0, r1 = n) is checked here when nothing is stated."""
     _cuda(adj)
     if adj.dtype != torch.float64 or adj.dim() != 2 or adj.stride(1) != 1:
         raise RuntimeError("cont2dist expects a row-major float64 CUDA matrix")
@@ -302,8 +338,10 @@ def cont2dist(adj: torch.Tensor, factor: float, want_f64: bool = True, want_f32:
     N.check(lib.hicgat_cont2dist_max_f64(adj.data_ptr(), adj.stride(0), n, r0, r1, float(factor), mx.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "hicgat_cont2dist_max_f64")
     if max_reduce is not None:
         max_reduce(mx)
+    if symmetric is None and want_f32 and r0 == 0 and r1 == n:
+        symmetric = asymmetry(adj) == 0.0
     o64 = torch.empty(r1 - r0, n, dtype=torch.float64, device=adj.device) if want_f64 else None
-    tgt = WishTarget.empty(n, r0, r1, adj.device) if want_f32 else None
+    tgt = WishTarget.empty(n, r0, r1, adj.device, symmetric) if want_f32 else None
     N.check(
         lib.hicgat_cont2dist_apply_f64(
             adj.data_ptr(), adj.stride(0), n, r0, r1, float(factor), mx.data_ptr(),

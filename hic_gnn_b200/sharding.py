@@ -143,13 +143,19 @@ def cuda_local_fn(target, mode: int, c_mse: float, c_l1: float):
     target (dense: hicgat_pairloss_fwd_bwd_packed in one launch; implicit/sparse: the split call + a pack)."""
     from .ops import SparseWishTarget, _PairWorkspace, _cuda, _stream, pairloss_raw
 
-    if isinstance(target, SparseWishTarget):
+    def sparse_fn_for(target, mode, c_mse, c_l1):
         def sparse_fn(coords: torch.Tensor, packed: torch.Tensor):
             m, g = pairloss_raw(coords, target, mode, c_mse, c_l1)
             packed[: N.PAIR_NMOM].copy_(m)
             packed[N.PAIR_NMOM:].copy_(g.reshape(-1))
 
         return sparse_fn
+
+    if isinstance(target, SparseWishTarget):
+        return sparse_fn_for(target, mode, c_mse, c_l1)
+
+    if target.symmetric is False:  # needs the row-side pass: go through the split call (ops.pairloss_raw) and pack
+        return sparse_fn_for(target, mode, c_mse, c_l1)
 
     def fn(coords: torch.Tensor, packed: torch.Tensor):
         _cuda(coords, packed)

@@ -128,7 +128,7 @@ def fit(model, x, graph, target: WishTarget, mode: str = "mse", lr: float = 1e-3
             pending.clear()
             for v in vals:
                 hist.append(v)
-                if abs(old - v) <= thresh:
+                if not (abs(old - v) > thresh):  # the reference loops `while lossdiff > thresh`: a NaN loss ends training
                     done = True
                 old = v
     return hist

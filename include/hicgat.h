@@ -131,6 +131,26 @@ HICGAT_API int hicgat_pairloss_sparse_fwd_bwd(const float* coords, const int32_t
                                    void* workspace, size_t workspace_bytes, hicgat_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Non-symmetric targets.  The fused kernels above take the column-side sum as the complete gradient,
+ * which needs t_ij = t_ji; the reference does not symmetrise `y` (utils.py:29-35, MSELoss over the full
+ * matrix at HiC-GNN_main.py:127; convert_to_matrix's triu + tril(mat.T, 1), utils.py:21, is asymmetric on
+ * the first off-diagonal for lists with lower-triangle records).
+ *   hicgat_asymmetry_f32/_f64: out_max[0] (device f64) = max |M_ij - M_ji| over i in [r0, r1), all j, of
+ *     the FULL row-major matrix `mat` (ld elements per row); +inf for a one-sided NaN.  Run once when a
+ *     target is built.
+ *   hicgat_pairloss_rowside_add: grad[i] += c * sum_j (d_ij - t_ij)/d_ij (x_i - x_j) for rows [r0, r1) of
+ *     the target block (layout as above): the ROW-side term of the MSE gradient.  For an asymmetric target
+ *     call hicgat_pairloss_fwd_bwd with c_mse = 2/n^2 and then this with c = 2/n^2 (autograd of MSELoss
+ *     over cdist gives exactly that sum); values and the i<j moments need no correction.
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API int hicgat_asymmetry_f32(const float* mat, int64_t ld, int64_t n, int64_t r0, int64_t r1, double* out_max,
+                         hicgat_stream_t stream);
+HICGAT_API int hicgat_asymmetry_f64(const double* mat, int64_t ld, int64_t n, int64_t r0, int64_t r1, double* out_max,
+                         hicgat_stream_t stream);
+HICGAT_API int hicgat_pairloss_rowside_add(const float* coords, const float* target, int64_t pitch, int64_t n, int64_t r0,
+                                int64_t r1, float c, float* grad, hicgat_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * (3) Exchange step of the row-sharded loss: one-shot all-reduce of every rank's partial
  * [8 x f64 moments | 3n x f32 gradient] (64 + 12n bytes, what hicgat_pairloss_fwd_bwd writes when
  * given moments = base and grad = base + 64 bytes) over NVLink peer memory.  No counterpart in

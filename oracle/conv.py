@@ -127,6 +127,26 @@ class GATConv(nn.Module):
             out = torch.zeros(n, H, C, dtype=x_l.dtype).index_add_(0, row, msg)
         return out.reshape(n, H * C) + self.bias
 
+    def forward_rows(self, x: torch.Tensor, csr: CSR, r1: int) -> torch.Tensor:
+        """Literal PyG message/aggregate order restricted to the TARGET rows ``[0, r1)`` (all source nodes):
+        output rows ``[0, r1)`` of :meth:`forward`.  Used by ``bench.py``'s CPU baseline on maps whose
+        E x H x C message tensor (what PyG materialises) does not fit host memory: cost is proportional to the
+        edges of the slice, so a slice timing extrapolates by edge count."""
+        H, C = self.heads, self.out_channels
+        x_l, alpha_l, alpha_r = self._project(x)
+        g = set_diag(csr)  # recomputed on every forward, like GATConv does
+        k1 = int(g.rowptr[r1])
+        row, col = g.row[:k1], g.col[:k1]
+        e = F.leaky_relu(alpha_l[col] + alpha_r[row], self.negative_slope)
+        idx = row.unsqueeze(1).expand(-1, H)
+        m = torch.full((r1, H), float("-inf"), dtype=e.dtype).scatter_reduce(0, idx, e, reduce="amax", include_self=True)
+        p = (e - m[row]).exp()
+        s = torch.zeros(r1, H, dtype=e.dtype).index_add_(0, row, p)
+        a = p / (s[row] + 1e-16)
+        msg = x_l[col] * a.unsqueeze(-1)
+        out = torch.zeros(r1, H, C, dtype=x_l.dtype).index_add_(0, row, msg)
+        return out.reshape(r1, H * C) + self.bias
+
     def attention(self, x: torch.Tensor, csr: CSR) -> torch.Tensor:
         """Per-edge attention coefficients [nnz+N, H] in ``set_diag`` CSR order."""
         x_l, alpha_l, alpha_r = self._project(x)

@@ -274,3 +274,78 @@ def test_full_size_c5_properties_and_row_sharding():
         g_sum += gb.double()
     assert rel_err(m_sum, m_full) < 1e-7
     assert rel_err(g_sum, g_full) < TOL
+
+
+# ------------------------------------------------------------------------------ non-symmetric targets
+def _asym_truth(n, seed):
+    """Wish matrix with t_ij != t_ji, as the reference can produce one (utils.load_input keeps `y` as
+    given, utils.py:29-35; convert_to_matrix's triu + tril(mat.T, 1), utils.py:21, is asymmetric on the
+    first off-diagonal for lists with lower-triangle records)."""
+    truth = wish_from_map(small_map(n, 0.6, seed=seed), 1.0)
+    g = torch.Generator().manual_seed(seed)
+    noise = 0.2 * torch.rand(n, n, generator=g, dtype=torch.float64)
+    truth = truth + torch.triu(noise, 1)      # upper triangle only: T != T^T
+    idx = torch.arange(n - 1)
+    truth[idx + 1, idx] *= 0.5                # and the first sub-diagonal, like the reference's list quirk
+    return truth
+
+
+@pytest.mark.parametrize("n", [5, 129, 700])
+def test_mse_asymmetric_target_matches_autograd(n):
+    """The column-side sum is the complete gradient only for t_ij = t_ji.  For an asymmetric truth the target
+    build detects it and the row-side term is added: loss, gradient AND the i<j moments must match the
+    oracle's autograd / scipy on the same matrix (1e-5)."""
+    import hic_gnn_b200 as hg
+    from hic_gnn_b200 import ops
+    from oracle import loss as oloss
+
+    truth = _asym_truth(n, seed=n)
+    assert float((truth - truth.t()).abs().max()) > 1e-3
+    coords = random_coords(n, seed=n + 7)
+    want_l, want_g = _oracle_mse(coords, truth)
+    tgt = hg.WishTarget.from_dense(truth.cuda())
+    assert tgt.symmetric is False
+    c = coords.cuda().requires_grad_(True)
+    loss, moments = hg.pairwise_loss(c, tgt, "mse_moments_full")
+    (g,) = torch.autograd.grad(loss, c)
+    assert abs(float(loss) - float(want_l)) / float(want_l) < TOL
+    assert rel_err(g.cpu(), want_g) < TOL
+    # what the symmetric fast path would have produced is measurably wrong here (the test has teeth)
+    tgt_wrong = hg.WishTarget.from_dense(truth.cuda(), symmetric=True)
+    _, g_wrong = ops.pairloss_raw(coords.cuda(), tgt_wrong, ops._MODES["mse"], 4.0 / n**2, 0.0)
+    assert rel_err(g_wrong.cpu(), want_g) > 1e-3
+    # moments follow the reference's triu gathers: t_ij with i < j
+    dist_truth, dist_out = oloss.triu_pairs(truth, coords)
+    d, t = dist_out.double(), dist_truth.double()
+    m = moments.cpu()
+    for k, want in [(4, t.sum()), (6, (d * t).sum()), (7, ((d - t) ** 2).sum())]:
+        assert abs(float(m[k]) - float(want)) / float(want) < TOL, k
+    # row blocks: every block adds its own row-side term
+    c_mse = 4.0 / n**2
+    g_sum = torch.zeros(n, 3, device="cuda")
+    cuts = [0, n // 3, n // 3, n]
+    for r0, r1 in zip(cuts[:-1], cuts[1:]):
+        blk = hg.WishTarget.from_dense(truth.cuda(), r0, r1)
+        assert blk.symmetric is False or r0 == r1
+        _, gb = ops.pairloss_raw(coords.cuda(), blk, ops._MODES["mse"], c_mse, 0.0)
+        g_sum += gb
+    assert rel_err(g_sum.cpu(), want_g) < TOL
+    with pytest.raises(NotImplementedError, match="symmetric"):
+        hg.pairwise_loss(c, tgt, "contrastive")
+
+
+def test_symmetry_check_on_reference_outputs(golden):
+    """Outputs of the reference's own code: cont2dist of the (symmetric) chr19 map is symmetric; the wish matrix of
+    the asymmetric `load_input` case and convert_to_matrix's `dup_matrix` are not (max |M - M^T| = 9 for the latter)."""
+    import hic_gnn_b200 as hg
+    from hic_gnn_b200 import ops, utils
+
+    g, _ = golden
+    assert hg.WishTarget.from_dense(torch.tensor(g["1mb_wish_1.0"]).cuda()).symmetric is True
+    assert ops.asymmetry(torch.tensor(g["dup_matrix"]).cuda()) == 9.0
+    asym = torch.tensor(g["asym_y"]).cuda()
+    want = float((asym - asym.t()).abs().max())
+    assert want > 0 and ops.asymmetry(asym) == want
+    assert utils.wish_target(asym, 1.0).symmetric is False
+    # an empty row block is trivially symmetric
+    assert ops.asymmetry(asym, 2, 2) == 0.0

@@ -61,3 +61,20 @@ def test_fit_batched_readback_overruns_by_less_than_one_batch(monkeypatch, check
 def test_unknown_mode_is_rejected():
     with pytest.raises(ValueError):
         train.TrainStep(_Model(), None, None, None, mode="spearman")
+
+
+def test_nan_loss_ends_training_like_the_reference():
+    """`while lossdiff > thresh` is False for a NaN difference: the reference stops after a divergence, and so must
+    fit() (an `abs(old - new) <= thresh` test would spin forever when max_steps is None)."""
+    import pytest as _pt
+
+    losses = [0.9, 0.5, float("nan"), 0.4, 0.3]
+    step = ScriptedStep(losses)
+    mp = _pt.MonkeyPatch()
+    try:
+        mp.setattr(train, "TrainStep", lambda *a, **k: step)
+        got = train.fit(_Model(), None, None, None, mode="mse", thresh=1e-8)
+    finally:
+        mp.undo()
+    assert len(got) == 3 and got[2] != got[2] and step.calls == 3
+    assert len(reference_loop(losses, 1e-8)) == 3
