@@ -399,6 +399,7 @@ constexpr int kCombineThreads = 512;
 // loads warm; pass 1 follows the wait (moment block of a 1 560-partial grid: 8.6 -> 5.4 us after the wait,
 // %globaltimer stamps; the gradient blocks did not change).
 __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const Params P, const float scale, const int want_grad, const int npass) {
+    pdl_launch_dependents();  // a consumer launched with programmatic serialization (the sharded exchange kernel) may become resident now
     const int tid = threadIdx.x;
     __shared__ double s_m[kCombineThreads / 32][kNM];
 #ifdef HICGAT_TRACE

@@ -70,48 +70,67 @@ class ShardedPairLoss:
 
 
 class P2PShardedPairLoss:
-    """Same contract as :class:`ShardedPairLoss`, but the exchange is the hand-written one-shot
-    all-reduce over NVLink peer memory (``hicgat_allreduce_partials_p2p``): the fused loss kernel
-    writes its partial ``[8 x f64 moments | 3n x f32 gradient]`` straight into a symmetric buffer
-    that every rank maps, then ONE kernel per rank does barrier + rank-ordered sum.  Two buffer
-    halves alternate by step parity (see csrc/comm.cu for why that makes a trailing barrier
-    unnecessary).  ``local_fn(coords, moments_f64[8], grad_f32[n,3])`` fills the local partial."""
+    """Same contract as :class:`ShardedPairLoss`, but the exchange is the hand-written two-shot all-reduce over
+    NVLink peer memory (``hicgat_allreduce_partials_twoshot``, csrc/comm.cu): the fused loss kernel writes its partial
+    ``[8 x f64 moments | 3n x f32 gradient]`` straight into a symmetric buffer that every rank maps; ONE kernel per rank
+    then does barrier -> reduce slice ``rank`` of all partials (rank order, f64) -> store it into every rank's result
+    buffer -> barrier.  The epoch counter lives in device memory, so every launch has identical arguments and the whole
+    sharded step (loss kernel + exchange) can be captured in a CUDA graph (``capturable``).  The returned gradient is
+    a view of this rank's result buffer: valid until the next call.
+    ``local_fn(coords, moments_f64[8], grad_f32[n,3])`` fills the local partial.
+    ``oneshot=True`` selects the older one-shot kernel (every rank reads all partials; host-side epoch, not capturable)."""
 
     SLOT_BASE = 256  # uint32 slot offset inside torch's signal pad (its own barriers use the low channels)
 
-    def __init__(self, n: int, local_fn, device, group=None, moment_const=None):
+    def __init__(self, n: int, local_fn, device, group=None, moment_const=None, oneshot: bool = False):
         import ctypes as C
 
         import torch.distributed._symmetric_memory as symm
 
         group = group if group is not None else dist.group.WORLD
-        self.n, self.local_fn = n, local_fn
-        self.half_bytes = (64 + 12 * n + 15) // 16 * 16
-        self.buf = symm.empty(2 * self.half_bytes, dtype=torch.uint8, device=device)
+        self.n, self.local_fn, self.oneshot = n, local_fn, oneshot
+        self.capturable = not oneshot
+        grad_bytes = (12 * n + 15) // 16 * 16
+        self.part_bytes = 64 + grad_bytes
+        # layout: [partial 0 | partial 1 (one-shot only: epoch parity) | result]
+        self.res_off = 2 * self.part_bytes
+        self.buf = symm.empty(self.res_off + grad_bytes, dtype=torch.uint8, device=device)
         self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, group)
         self.world, self.rank = self.hdl.world_size, self.hdl.rank
-        if self.hdl.signal_pad_size < 4 * (self.SLOT_BASE + self.world):
+        if self.hdl.signal_pad_size < 4 * (self.SLOT_BASE + 64):
             raise RuntimeError("symmetric-memory signal pad too small")
-        self._bufs = (C.c_uint64 * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._bufs = (C.c_uint64 * self.world)(*ptrs)
+        self._res = (C.c_uint64 * self.world)(*[p + self.res_off for p in ptrs])
         self._pads = (C.c_uint64 * self.world)(*[int(p) for p in self.hdl.signal_pad_ptrs])
         self.moment_const = moment_const
-        # typed views of the two halves of the local partial
-        self.part_m = [self.buf[h * self.half_bytes: h * self.half_bytes + 64].view(torch.float64) for h in range(2)]
-        self.part_g = [self.buf[h * self.half_bytes + 64: h * self.half_bytes + 64 + 12 * n].view(torch.float32).view(n, 3) for h in range(2)]
+        # typed views of the local partial(s) and of the result
+        self.part_m = [self.buf[h * self.part_bytes: h * self.part_bytes + 64].view(torch.float64) for h in range(2)]
+        self.part_g = [self.buf[h * self.part_bytes + 64: h * self.part_bytes + 64 + 12 * n].view(torch.float32).view(n, 3) for h in range(2)]
+        self.res_g = self.buf[self.res_off: self.res_off + 12 * n].view(torch.float32).view(n, 3)
         self.out_m = [torch.empty(N.PAIR_NMOM, dtype=torch.float64, device=device) for _ in range(2)]
         self.out_g = [torch.empty(n, 3, dtype=torch.float32, device=device) for _ in range(2)]
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)  # [epoch, ticket, ticket, -]: maintained by the kernel
         self.epoch = 0
         torch.cuda.synchronize(device)
         dist.barrier(group)  # every rank's buffer is zeroed and mapped before the first signal
 
     def __call__(self, coords: torch.Tensor):
+        if not self.oneshot:
+            self.local_fn(coords, self.part_m[0], self.part_g[0])
+            rc = N.lib().hicgat_allreduce_partials_twoshot(
+                self._bufs, self._res, self._pads, self.rank, self.world, self.n, self.SLOT_BASE + 32, self.state.data_ptr(),
+                None if self.moment_const is None else self.moment_const.data_ptr(), self.out_m[0].data_ptr(), torch.cuda.current_stream().cuda_stream,
+            )
+            N.check(rc, "hicgat_allreduce_partials_twoshot")
+            return self.out_m[0], self.res_g
         self.epoch += 1
         par = self.epoch & 1
         self.local_fn(coords, self.part_m[par], self.part_g[par])
         m, g = self.out_m[par], self.out_g[par]
         rc = N.lib().hicgat_allreduce_partials_p2p(
-            self._bufs, self._pads, self.rank, self.world, self.n, par * self.half_bytes, self.SLOT_BASE, self.epoch & 0xFFFFFFFF,
+            self._bufs, self._pads, self.rank, self.world, self.n, par * self.part_bytes, self.SLOT_BASE, self.epoch & 0xFFFFFFFF,
             None if self.moment_const is None else self.moment_const.data_ptr(), m.data_ptr(), g.data_ptr(),
             torch.cuda.current_stream().cuda_stream,
         )
@@ -120,20 +139,20 @@ class P2PShardedPairLoss:
 
 
 def make_sharded_pair_loss(n: int, local_fn, device, group=None, moment_const=None, transport: str = "auto", local_split_fn=None):
-    """``transport``: ``"p2p"`` (one-shot kernel over NVLink peer memory; needs ``local_split_fn``),
-    ``"nccl"`` (packed ``all_reduce``; uses ``local_fn``) or ``"auto"`` (p2p on CUDA with an
-    initialised multi-rank NCCL group when the symmetric-memory rendezvous succeeds, else nccl)."""
+    """``transport``: ``"p2p"`` (two-shot kernel over NVLink peer memory; needs ``local_split_fn``), ``"p2p_oneshot"``
+    (the older one-shot kernel, A/B only), ``"nccl"`` (packed ``all_reduce``; uses ``local_fn``) or ``"auto"`` (p2p on CUDA
+    with an initialised multi-rank NCCL group when the symmetric-memory rendezvous succeeds, else nccl)."""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    if local_split_fn is not None and (transport == "p2p" or (transport == "auto" and multi and torch.device(device).type == "cuda")):
+    if local_split_fn is not None and (transport in ("p2p", "p2p_oneshot") or (transport == "auto" and multi and torch.device(device).type == "cuda")):
         try:
-            return P2PShardedPairLoss(n, local_split_fn, device, group, moment_const)
+            return P2PShardedPairLoss(n, local_split_fn, device, group, moment_const, oneshot=transport == "p2p_oneshot")
         except Exception as e:  # no symmetric memory on this system: the NCCL exchange is equivalent
-            if transport == "p2p":
+            if transport in ("p2p", "p2p_oneshot"):
                 raise
             import warnings
 
             warnings.warn(f"symmetric-memory exchange unavailable ({e!r}); using the NCCL all-reduce")
-    elif transport == "p2p":
+    elif transport in ("p2p", "p2p_oneshot"):
         raise RuntimeError("transport='p2p' needs local_split_fn")
     return ShardedPairLoss(n, local_fn, device, group, moment_const)
 

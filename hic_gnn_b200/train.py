@@ -61,6 +61,11 @@ class TrainStep:
             raise ValueError(mode)
         if mode == "mse_spearman" and use_cuda_graph:
             raise ValueError("mse_spearman reads the rank correlation back every step: it cannot be captured in a CUDA graph")
+        if use_cuda_graph and reducer is not None and not getattr(reducer, "capturable", False):
+            # a captured launch replays its arguments: an exchange that takes the epoch / buffer parity from the host (the
+            # one-shot p2p kernel) or runs a NCCL collective outside torch's graph support would reuse one epoch forever
+            raise ValueError("use_cuda_graph needs a capturable sharded reducer (the default two-shot p2p exchange); "
+                             f"{type(reducer).__name__} takes per-step host arguments")
         self.model, self.x, self.graph, self.target, self.mode, self.reducer, self.alpha = model, x, graph, target, mode, reducer, alpha
         self.optimizer = Adam(model.parameters(), lr=lr, capturable=use_cuda_graph)
         self.total = None

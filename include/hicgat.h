@@ -168,6 +168,22 @@ HICGAT_API int hicgat_allreduce_partials_p2p(const uint64_t* peer_bufs_host, con
                                   const double* moment_const, double* out_moments, float* out_grad,
                                   hicgat_stream_t stream);
 
+/* Two-shot variant (default exchange): reduce-scatter + all-gather inside ONE kernel.  Rank r holds its partial
+ * [8 x f64 moments | 3n x f32 gradient] at peer_partials_host[r] and receives the reduced gradient (3n x f32) at
+ * peer_results_host[r]; both live in symmetric memory, both padded to a multiple of 16 bytes with the padding zeroed.
+ * After a first barrier rank r sums slice r of all partials (rank order, f64 accumulation, rounded once) and stores it
+ * into every rank's result buffer; a second barrier completes the all-gather.  2 x 12n bytes per rank cross NVLink
+ * (world x 12n for the one-shot kernel), results are bit-identical on every rank, and no buffer needs double
+ * buffering (a rank leaves the kernel only after every peer has finished reading its partial).  `state` = uint32[4]
+ * in LOCAL device memory, zero-initialised once: [0] epoch (maintained by the kernel), [1], [2] block tickets; signal
+ * slots slot_base .. slot_base + 31 of every pad are used.  All arguments are the same on every call, so the launch
+ * can be captured in a CUDA graph; it uses programmatic stream serialization (griddepcontrol.wait on entry).
+ * moments f64[8] (+ moment_const if not NULL) are written to out_moments (ordinary local memory). */
+HICGAT_API int hicgat_allreduce_partials_twoshot(const uint64_t* peer_partials_host, const uint64_t* peer_results_host,
+                                      const uint64_t* signal_pads_host, int rank, int world, int64_t n, int slot_base,
+                                      uint32_t* state, const double* moment_const, double* out_moments,
+                                      hicgat_stream_t stream);
+
 /* Materialising variant kept for API parity of model.forward() (returns the N x N matrix,
  * models.py:39): dist[i,j] = |x_i - x_j|, and its backward
  * grad_coords[i] = sum_j (G[i,j] + G[j,i]) (x_i - x_j)/d_ij  (ATen _euclidean_dist_backward). */

@@ -316,8 +316,8 @@ def test_per_step_loss_and_gradients_along_oracle_trajectory(cls, mode, n, densi
     target = gutils.wish_target(gdata.y, 1.0)
     opt = torch.optim.Adam(om.parameters(), lr=1e-3)
     watch = _KinkWatch(om, cls)
-    strict_steps = 0
-    violations = []
+    strict_steps = ok_steps = 0
+    violations, kink_violations = [], []
     for s in range(steps):
         gm.load_state_dict(om.state_dict())
         # reference gradients of the f64-evaluated formula
@@ -359,9 +359,8 @@ def test_per_step_loss_and_gradients_along_oracle_trajectory(cls, mode, n, densi
             assert abs(float(pearson_from_moments(moments, n * (n - 1) / 2)) - r64) < 1e-6
             want_total, _, r, _ = oloss.mse_pearson_loss(coords_o.detach(), truth)  # as the reference evaluates it (f32)
             assert abs(float(total) - float(want_total)) / abs(float(want_total)) < max(TOL, 2 * abs(float(want_total) - total64) / abs(total64))
+        step_ok = True
         for name, p in gm.named_parameters():
-            if not strict:
-                break
             want = g64[name]
             if want is None:
                 assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
@@ -374,15 +373,21 @@ def test_per_step_loss_and_gradients_along_oracle_trajectory(cls, mode, n, densi
             e_gpu = rel_err(p.grad, want)
             e_ref = rel_err(g32[name], want)
             if not e_gpu < max(2e-5, e_ref):
-                violations.append((s, name, e_gpu, e_ref, watch.gap))
+                step_ok = False
+                (violations if strict else kink_violations).append((s, name, e_gpu, e_ref, watch.gap))
+        ok_steps += step_ok
         opt.step()
     watch.close()
-    assert strict_steps >= steps // 3, strict_steps
-    # A kernel bug violates the bound at every step.  One isolated step may still lose a (Leaky)ReLU unit to
-    # the kink (the 5e-7 gap filter is a heuristic; the oracle's own f32 forward depends on its thread
-    # count): tolerated if it stays kink-sized (< 1e-2 of the tensor's max).
+    # A kernel bug violates the 2e-5 bound at EVERY step.  How many steps are "strict" (no unit within 5e-7 of its
+    # activation kink) depends on the host: the oracle's f32 forward rounds differently with the CPU thread count, and
+    # with ~2e5 pre-activations per forward a near-kink unit is the rule rather than the exception.  So: (i) every
+    # step is compared; (ii) in strict steps at most one isolated step may lose a unit to the kink (the gap filter is
+    # a heuristic), kink-sized (< 1e-2 of the tensor's max); (iii) in non-strict steps a violation must be kink-sized;
+    # (iv) at least half of all steps meet the 2e-5 bound on every parameter tensor.
     bad_steps = sorted({v[0] for v in violations})
     assert len(bad_steps) <= 1 and all(v[2] < 1e-2 for v in violations), violations[:6]
+    assert all(v[2] < 1e-2 for v in kink_violations), kink_violations[:6]
+    assert ok_steps >= steps // 2, (ok_steps, strict_steps, violations[:3], kink_violations[:3])
 
 
 @pytest.mark.parametrize("cls,mode,n,density", _TRAJ_CASES)

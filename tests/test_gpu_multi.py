@@ -28,9 +28,9 @@ def _worker(rank, world, port, n, tmpdir):
         _, full = ops.cont2dist(adj, 1.0, want_f64=False, want_f32=True)
         assert torch.equal(tgt.dense(), full.dense()[r0:r1])
         for mode, transport in [("mse", "nccl"), ("mse_moments", "nccl"), ("contrastive", "nccl"),
-                                ("mse", "p2p"), ("mse_moments", "p2p"), ("contrastive", "p2p")]:
+                                ("mse", "p2p"), ("mse_moments", "p2p"), ("contrastive", "p2p"), ("mse_moments", "p2p_oneshot")]:
             red = ops.sharded_reducer(tgt, mode, transport=transport)
-            if transport == "p2p":  # several steps: exercises the epoch / buffer-parity protocol
+            if transport != "nccl":  # several steps: exercises the (device-side) epoch / barrier protocol
                 for _ in range(5):
                     hg.pairwise_loss(coords, tgt, mode, reducer=red)
             loss_s, mom_s = hg.pairwise_loss(coords, tgt, mode, reducer=red)
@@ -58,6 +58,26 @@ def _worker(rank, world, port, n, tmpdir):
             (g_1,) = torch.autograd.grad(loss_1, coords)
             assert abs(float(loss_s) - float(loss_1)) <= 1e-6 * abs(float(loss_1)), (transport, float(loss_s), float(loss_1))
             assert rel_err(mom_s, mom_1) < 1e-6 and rel_err(g_s, g_1) < 1e-5
+        # whole sharded training step (replicated GAT net, row-sharded loss, two-shot exchange) captured in ONE CUDA graph:
+        # the exchange takes its epoch from device memory, so replays stay in step; must follow the eager sharded loop
+        from hic_gnn_b200 import models, train
+
+        x = synth.synthetic_features(n, seed=3).cuda()
+        hist = {}
+        for graphed in (False, True):
+            torch.manual_seed(42)
+            model = models.GATNetSelectiveResidualsUpdated().cuda()
+            red = ops.sharded_reducer(tgt, "mse_moments", transport="p2p")
+            step = train.TrainStep(model, x, data.edge_index, tgt, mode="mse_pearson", lr=1e-3, use_cuda_graph=graphed, reducer=red)
+            hist[graphed] = [float(step()[0]) for _ in range(6)]
+            sd = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+            gathered = [torch.empty_like(sd) for _ in range(world)]
+            dist.all_gather(gathered, sd)
+            assert all(torch.equal(gathered[0], t) for t in gathered), "replicas diverged"
+        assert abs(hist[True][0] - hist[False][0]) <= 1e-6 * abs(hist[False][0]), hist
+        assert all(abs(a - b) <= 1e-2 * abs(b) for a, b in zip(hist[True], hist[False])), hist  # capturable Adam rounds its bias corrections differently
+        with pytest.raises(ValueError, match="capturable"):
+            train.TrainStep(model, x, data.edge_index, tgt, mode="mse_pearson", use_cuda_graph=True, reducer=ops.sharded_reducer(tgt, "mse_moments", transport="nccl"))
         open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
