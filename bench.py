@@ -81,7 +81,8 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="pair-loss kernel: 0 = TMA tile ring (default), 1 = per-lane streaming loads")
     ap.add_argument("--rows-per-cta", type=int, default=0, help="pair-loss row-chunk override (0 = library default)")
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "p2p_oneshot", "nccl"], help="exchange of the sharded loss partials")
-    ap.add_argument("--emulate-world", type=int, default=0, help="profiling aid: on ONE GPU run rank 0's row block of a W-way split (not a bench line)")
+    ap.add_argument("--emulate-world", type=int, default=0, help="profiling aid: on ONE GPU run one rank's row block of a W-way split (not a bench line)")
+    ap.add_argument("--emulate-rank", type=int, default=0, help="which rank's block --emulate-world runs")
     ap.add_argument("--no-measure-copy", dest="measure_copy", action="store_false", help="skip the same-process copy-bandwidth control")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the training step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-sparse", action="store_true", help="skip the implicit-target (row f-4) leg")
@@ -522,9 +523,10 @@ def build_inputs(env: Env, name: str, want_graph: bool, want_cpu_rows: int):
         adj.fill_diagonal_(0)
     else:
         adj = synth.synthetic_map_chunked(n, w["density"], device=dev)
-    r0, r1 = sharding.row_block(n, env.rank, env.world)
+    balance = "upper" if ops._USE_UPPER else "rows"  # symmetric targets stream only the upper triangle: balance the blocks by its area
+    r0, r1 = sharding.row_block(n, env.rank, env.world, balance)
     if env.args.emulate_world and env.world == 1:
-        r0, r1 = sharding.row_block(n, 0, env.args.emulate_world)
+        r0, r1 = sharding.row_block(n, env.args.emulate_rank, env.args.emulate_world, balance)
     # the maps are symmetric by construction (synth) / checked by the tests (fixtures): stated, not re-checked per rank
     _, target = ops.cont2dist(adj[r0:r1], w["factor"], want_f64=False, want_f32=True, r0=r0, r1=r1, max_reduce=sharding.allreduce_max_, symmetric=True)
     graph = None
@@ -547,7 +549,7 @@ def build_inputs(env: Env, name: str, want_graph: bool, want_cpu_rows: int):
         out["cpu_truth"] = cpu_truth.cpu()
         if n <= 3000:
             out["adj_cpu"] = adj.cpu().numpy()
-    out.update({"adj": adj, "target": target, "graph": graph, "r0": r0, "r1": r1})
+    out.update({"adj": adj, "target": target, "graph": graph, "r0": r0, "r1": r1, "balance": balance})
     return out
 
 
@@ -657,10 +659,17 @@ def measure_workload(env: Env, name: str, primary: bool):
     mse = float(moments[0]) / (float(n) * float(n))
     env.windows[f"loss_{name}" if not primary else "loss"] = (w0, w1)
     peak, peak_src = peak_hbm()
-    achieved = nloc * n * 4.0 / (kern_ms * 1e-3) / 1e9
+    upper = ops.uses_upper_triangle(target)
+    shards = args.emulate_world if (args.emulate_world and world == 1) else world
+    # algorithmic bytes: 4 B per ordered pair of this rank's share; in upper-triangle mode the share is 1/shards of
+    # the pairs (blocks are balanced by area) and the kernel actually streams about half of that (2 B per ordered pair)
+    alg_bytes = (float(n) * float(n) / shards if upper else float(nloc) * n) * 4.0
+    streamed = (sum(n - i for i in (r0, r1 - 1)) / 2.0 * (r1 - r0) if r1 > r0 else 0.0) * 4.0 if upper else float(nloc) * n * 4.0
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     res = {"name": name, "n": n, "K": K, "W": W, "value": value, "ms_per_step": elapsed_ms / K, "kernel_ms": kern_ms, "exchange_ms": exch_ms, "launches": int(launches),
            "attempts": attempts, "mse": mse, "nloc": nloc, "target_bytes": target_bytes, "transport": transport, "setup_s": round(t_setup, 1),
-           "achieved": achieved, "peak": peak, "peak_src": peak_src, "loss_mode": loss_mode}
+           "achieved": achieved, "peak": peak, "peak_src": peak_src, "loss_mode": loss_mode, "upper": upper, "alg_bytes": alg_bytes, "streamed_bytes": streamed,
+           "rows": [r0, r1], "balance": inp["balance"]}
 
     # ---- (1b) the other per-step mode of the training loops (MSE + Pearson moments in the same pass), briefly
     if primary and loss_mode == "mse":
@@ -689,7 +698,8 @@ def measure_workload(env: Env, name: str, primary: bool):
         host_coords = torch.empty(n, 3, dtype=torch.float32, pin_memory=True)
         host_coords.copy_(coords)
         hp = ops.HostPairLoss(n, r0, r1, block_rows=max(64, min(4096, (256 << 20) // (target.pitch * 4))), device=dev,
-                              reduce=sharding.allreduce_packed if world > 1 else None)  # host-buffer path: NCCL exchange
+                              reduce=sharding.allreduce_packed if world > 1 else None,  # host-buffer path: NCCL exchange
+                              symmetric=upper)  # symmetric target: only the upper-triangle columns of every row block cross PCIe
         for _ in range(2):
             hm, hgrad = hp(host_coords, host_target, mode, c_mse, c_l1)
         barrier()
@@ -706,7 +716,8 @@ def measure_workload(env: Env, name: str, primary: bool):
         e2e = {"value": float(n) * float(n) * Ke / (e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(hp.d2h_bytes), "steps": Ke, "ms_per_step": e_ms / Ke,
                "h2d_gbs": h2d / (e_ms / Ke * 1e-3) / 1e9,
-               "note": "per rank: coords + this rank's f32 target rows from pinned host memory every step (PCIe-bound by construction)"}
+               "note": "per rank: coords + this rank's f32 target rows from pinned host memory every step (PCIe-bound by construction)"
+                       + ("; the target is symmetric, so only the columns at or right of each row block's diagonal are copied" if upper else "")}
         del host_target, hp
         torch.cuda.empty_cache()
         # (2b) the training-loop variant of the same call: the target stays resident (uploaded once, like
@@ -895,7 +906,9 @@ def compact(res):
     out = {"workload": WORKLOADS[res["name"]]["desc"], "n_loci": n, "pairs_per_step": float(n) * float(n),
            "loss": {"value": res["value"], "unit": UNIT, "ms_per_step": res["ms_per_step"], "kernel_ms": res["kernel_ms"], "exchange_ms": res["exchange_ms"],
                     "steps": res["K"], "loss_mode": res["loss_mode"], "rows_per_rank": res["nloc"],
-                    "roofline": {"bound": "hbm", "achieved": res["achieved"], "peak": peak, "unit": "GB/s", "frac": res["achieved"] / peak, "note": l2_note}},
+                    "rows": res["rows"], "upper_triangle_only": res["upper"],
+                    "roofline": {"bound": "hbm", "achieved": res["achieved"], "peak": peak, "unit": "GB/s", "frac": res["achieved"] / peak, "algorithmic_bytes": res["alg_bytes"],
+                                 "streamed_bytes": res["streamed_bytes"], "note": l2_note}},
            "train": res["train"], "cpu_baseline": res["cpu"], "check": {"mse": res["mse"]}}
     return out
 
@@ -960,14 +973,18 @@ def run_native(args):
             "data": "synthetic" if w["kind"] == "synthetic" else "reference fixture (chr19)",
             "config": workload_config(name, res["loss_mode"]),
             "run": {"parallelism": f"rows{world}" if world > 1 else ("single" if not args.emulate_world else f"rank0-of-{args.emulate_world} (emulated, NOT a bench line)"),
-                    "rows_per_rank": nloc, "cpus_near_gpu": env.numa, "exchange": res["transport"], "exchange_ms": res["exchange_ms"],
+                    "rows_per_rank": nloc, "rows": res["rows"], "row_balance": res["balance"], "upper_triangle_only": res["upper"], "cpus_near_gpu": env.numa, "exchange": res["transport"], "exchange_ms": res["exchange_ms"],
                     "timed_attempts": res["attempts"], "l2": f"no flush: each step streams {res['target_bytes'] / 1e6:.0f} MB of target per rank (L2 is 126 MB)",
                     "setup_s": res["setup_s"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": ("pairloss_tma_kernel" if args.variant == 0 else "pairloss_ldg_kernel") + " + pairloss_combine_kernel", "kernel_ms": kern_ms,
                          "note": "kernel_ms = CUDA events around the two launches of one loss evaluation; peak is a COPY bandwidth (half reads, half writes): a read-only stream can exceed it slightly; "
                                  "traffic = dram bytes of the committed ncu capture of this shape (profiles/pairloss_traffic.json), not re-measured in this run",
-                         "algorithmic_bytes": nloc * n * 4.0, "peak_source": res["peak_src"], "frac_of_spec_8000": achieved / 8000.0,
+                         "algorithmic_bytes": res["alg_bytes"], "streamed_bytes": res["streamed_bytes"],
+                         "streamed_note": "upper-triangle mode: the target is symmetric, the kernel reads ~2 B per ordered pair (column >= row only) and evaluates every unordered pair once; "
+                                          "`achieved` stays the ALGORITHMIC 4 B per ordered pair / kernel time (SURVEY.md 8d), so frac > 1 is the symmetry gain; streamed_bytes / kernel time is the DRAM-side rate" if res["upper"] else None,
+                         "streamed_gbs": res["streamed_bytes"] / (kern_ms * 1e-3) / 1e9,
+                         "peak_source": res["peak_src"], "frac_of_spec_8000": achieved / 8000.0,
                          "copy_gbs_this_run": copy_gbs, "frac_of_copy_this_run": (achieved / copy_gbs) if copy_gbs else None},
             "cpu_baseline": res["cpu"],
             "e2e": res["e2e"],

@@ -21,7 +21,9 @@ SIGNATURES = {
     "hicgat_version": (C.c_int, []),
     "hicgat_last_error": (C.c_char_p, []),
     "hicgat_launch_count": (C.c_uint64, []),
+    "hicgat_memcpy2d_h2d_async": (C.c_int, [_p, _sz, _p, _sz, _sz, _sz, _p]),
     "hicgat_pairloss_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "hicgat_pairloss_workspace_bytes_mode": (_sz, [_i64, _i64, _i64, _u32]),
     "hicgat_pairloss_fwd_bwd": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _p, _sz, _p]),
     "hicgat_pairloss_fwd_bwd_packed": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _sz, _p]),
     "hicgat_pairloss_set_tuning": (C.c_int, [_i32, _i32]),
@@ -66,7 +68,7 @@ SIGNATURES = {
     "hicgat_gat_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
-PAIR_GRAD_MSE, PAIR_GRAD_L1, PAIR_MOMENTS, PAIR_MOMENTS_D, PAIR_WS_CLEAN, PAIR_NMOM = 1, 2, 4, 8, 16, 8
+PAIR_GRAD_MSE, PAIR_GRAD_L1, PAIR_MOMENTS, PAIR_MOMENTS_D, PAIR_WS_CLEAN, PAIR_SYMMETRIC, PAIR_NMOM = 1, 2, 4, 8, 16, 32, 8
 
 _lib = None
 

@@ -113,9 +113,16 @@ __device__ __forceinline__ f2 grad_weight(f2 e, f2 rs, float c_mse, float c_l1) 
 // matching ATen's "ratio = 0 where dist == 0") at the cost of nothing: it rides in the first FMA.
 #define HICGAT_TINY2 0x0DA242600DA24260ull /* (1e-30f, 1e-30f) */
 
+// Row-side accumulators of ONE row (symmetric / upper-triangle mode): sum over the lane's columns of w * (x_j - x_i).
+struct RowAcc {
+    f2 x, y, z;
+};
+
 // One row x one column pair, no masks.  UPPER: this (row, pair) lies strictly above the diagonal.
-template <uint32_t MODE, bool UPPER>
-__device__ __forceinline__ void pair_fast(Acc& a, int p, f2 xjx, f2 xjy, f2 xjz, f2 xix, f2 xiy,
+// ROWS: upper-triangle mode -- every unordered pair is evaluated once, so the weight also feeds the row-side
+// accumulators and the strictly-upper sum of squares is kept apart (it counts twice in the full-matrix loss).
+template <uint32_t MODE, bool UPPER, bool ROWS>
+__device__ __forceinline__ void pair_fast(Acc& a, RowAcc& ra, int p, f2 xjx, f2 xjy, f2 xjz, f2 xix, f2 xiy,
                                           f2 xiz, f2 t, float c_mse, float c_l1) {
     f2 dx = f2_sub(xjx, xix), dy = f2_sub(xjy, xiy), dz = f2_sub(xjz, xiz);
     f2 d2 = f2_fma(dx, dx, f2_fma(dy, dy, f2_fma(dz, dz, HICGAT_TINY2)));
@@ -125,13 +132,18 @@ __device__ __forceinline__ void pair_fast(Acc& a, int p, f2 xjx, f2 xjy, f2 xjz,
     f2 d = f2_mul(d2, rs);
     f2 e = f2_sub(d, t);
     constexpr bool kMom = UPPER && (MODE & (kMomFull | kMomLight));
-    if constexpr (kMom) a.seu = f2_fma(e, e, a.seu);
+    if constexpr (kMom || (UPPER && ROWS)) a.seu = f2_fma(e, e, a.seu);
     else a.see = f2_fma(e, e, a.see);
     if constexpr ((MODE & 3u) != 0) {
         f2 w = grad_weight<MODE>(e, rs, c_mse, c_l1);
         a.gx[p] = f2_fma(w, dx, a.gx[p]);
         a.gy[p] = f2_fma(w, dy, a.gy[p]);
         a.gz[p] = f2_fma(w, dz, a.gz[p]);
+        if constexpr (ROWS) {
+            ra.x = f2_fma(w, dx, ra.x);
+            ra.y = f2_fma(w, dy, ra.y);
+            ra.z = f2_fma(w, dz, ra.z);
+        }
     }
     if constexpr (kMom) {
         a.sd = f2_add(a.sd, d);
@@ -149,9 +161,9 @@ __device__ __forceinline__ void pair_fast(Acc& a, int p, f2 xjx, f2 xjy, f2 xjz,
 }
 
 // Masked variant for edge strips (columns >= n), partial tiles and diagonal-crossing groups.
-// mv: 1 for valid (row, column); mu: 1 where additionally row < col.
-template <uint32_t MODE>
-__device__ __forceinline__ void pair_masked(Acc& a, int p, f2 xjx, f2 xjy, f2 xjz, f2 xix, f2 xiy,
+// mv: 1 for valid (row, column) -- in upper-triangle mode additionally row <= column; mu: 1 where row < col.
+template <uint32_t MODE, bool ROWS>
+__device__ __forceinline__ void pair_masked(Acc& a, RowAcc& ra, int p, f2 xjx, f2 xjy, f2 xjz, f2 xix, f2 xiy,
                                             f2 xiz, f2 t, f2 mv, f2 mu, float c_mse, float c_l1) {
     f2 dx = f2_sub(xjx, xix), dy = f2_sub(xjy, xiy), dz = f2_sub(xjz, xiz);
     f2 d2 = f2_fma(dx, dx, f2_fma(dy, dy, f2_fma(dz, dz, HICGAT_TINY2)));
@@ -166,22 +178,30 @@ __device__ __forceinline__ void pair_masked(Acc& a, int p, f2 xjx, f2 xjy, f2 xj
         a.gx[p] = f2_fma(w, dx, a.gx[p]);
         a.gy[p] = f2_fma(w, dy, a.gy[p]);
         a.gz[p] = f2_fma(w, dz, a.gz[p]);
+        if constexpr (ROWS) {
+            ra.x = f2_fma(w, dx, ra.x);
+            ra.y = f2_fma(w, dy, ra.y);
+            ra.z = f2_fma(w, dz, ra.z);
+        }
     }
-    if constexpr (kMom) {
-        f2 eu = f2_mul(e, mu), du = f2_mul(d, mu), tu = f2_mul(t, mu);
+    if constexpr (kMom || ROWS) {
+        f2 eu = f2_mul(e, mu);
         f2 el = f2_sub(e, eu);  // the part of e not under the upper mask
         a.see = f2_fma(el, el, a.see);
         a.seu = f2_fma(eu, eu, a.seu);
-        a.sd = f2_add(a.sd, du);
-        a.sdd = f2_fma(du, du, a.sdd);
-        a.sdt = f2_fma(du, tu, a.sdt);
-        if constexpr ((MODE & kMomFull) != 0) {
-            float ea, eb;
-            f2_unpack(eu, ea, eb);
-            a.sabs0 += fabsf(ea);
-            a.sabs1 += fabsf(eb);
-            a.st = f2_add(a.st, tu);
-            a.stt = f2_fma(tu, tu, a.stt);
+        if constexpr (kMom) {
+            f2 du = f2_mul(d, mu), tu = f2_mul(t, mu);
+            a.sd = f2_add(a.sd, du);
+            a.sdd = f2_fma(du, du, a.sdd);
+            a.sdt = f2_fma(du, tu, a.sdt);
+            if constexpr ((MODE & kMomFull) != 0) {
+                float ea, eb;
+                f2_unpack(eu, ea, eb);
+                a.sabs0 += fabsf(ea);
+                a.sabs1 += fabsf(eb);
+                a.st = f2_add(a.st, tu);
+                a.stt = f2_fma(tu, tu, a.stt);
+            }
         }
     } else {
         a.see = f2_fma(e, e, a.see);
@@ -209,6 +229,11 @@ struct Params {
     double* grad64;        // optional f64 copy of grad (packed all-reduce buffer)
     float* gpart;          // [nchunks][nstrips][384]  per-CTA gradient partials
     double* mpart;         // [nchunks*nstrips][kNM]   per-CTA moment partials
+    // upper-triangle ("symmetric") mode: only pairs with row <= column are evaluated; every CTA also emits the ROW-side
+    // gradient sums of its rows over its 128 columns: rpart[strip][(row - r0) * 3 + comp], rpitch floats per strip
+    int upper;
+    int64_t rpitch;
+    float* rpart;
 };
 
 struct ColumnRegs {
@@ -243,11 +268,35 @@ struct XiAddr {  // x_i rows behind 32-bit shared-space addresses (TMA variant)
     __device__ __forceinline__ void load(int u, float4& oxy, float2& oz) const;
 };
 
-template <uint32_t MODE, typename XI>
+// Transpose-reduce of the 24 row-side sums of one 8-row group (v[3 * u + comp]) across the warp: 24 shuffles instead of
+// 24 x 5.  On return lane L holds the warp total of slot  12*b4 + 6*b3 + 3*b2 + (b0 ? 2 : b1)  (b_k = bit k of L);
+// lanes with b0 = 1 hold their slot twice (b1 = 0 and b1 = 1).  Fixed order: bit-reproducible.
+__device__ __forceinline__ float row_butterfly(const float (&v)[3 * kU], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+    float w12[12], w6[6], w3[3];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) w12[k] = (b4 ? v[k + 12] : v[k]) + __shfl_xor_sync(0xffffffffu, b4 ? v[k] : v[k + 12], 16);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w6[k] = (b3 ? w12[k + 6] : w12[k]) + __shfl_xor_sync(0xffffffffu, b3 ? w12[k] : w12[k + 6], 8);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w3[k] = (b2 ? w6[k + 3] : w6[k]) + __shfl_xor_sync(0xffffffffu, b2 ? w6[k] : w6[k + 3], 4);
+    const float a = (b1 ? w3[1] : w3[0]) + __shfl_xor_sync(0xffffffffu, b1 ? w3[0] : w3[1], 2);
+    const float b = w3[2] + __shfl_xor_sync(0xffffffffu, w3[2], 2);
+    return (b0 ? b : a) + __shfl_xor_sync(0xffffffffu, b0 ? a : b, 1);
+}
+__device__ __forceinline__ int row_butterfly_slot(int lane) {
+    return ((lane & 16) ? 12 : 0) + ((lane & 8) ? 6 : 0) + ((lane & 4) ? 3 : 0) + ((lane & 1) ? 2 : ((lane & 2) ? 1 : 0));
+}
+
+// ROWS (upper-triangle mode): `rowdst` points at the 3 * kU row-side partials of this group's rows for this strip;
+// the group is never strictly below the diagonal (the CTA's row range is clipped at the strip's last column).
+template <uint32_t MODE, bool ROWS, typename XI>
 __device__ __forceinline__ void process_group(Acc& a, const ColumnRegs& c, const float4 (&t)[kU], const XI xi,
                                               int rows_here, int rg, int col0, int n, bool edge,
-                                              int strip_lo, int strip_hi, float c_mse, float c_l1) {
+                                              int strip_lo, int strip_hi, float c_mse, float c_l1, float* __restrict__ rowdst, int lane) {
     const bool fast = !edge && rows_here == kU;
+    constexpr bool kRowGrad = ROWS && (MODE & 3u) != 0;
+    float rv[kRowGrad ? 3 * kU : 1];
     if (fast && rg + kU - 1 < strip_lo) {  // strictly above the diagonal
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
@@ -255,22 +304,28 @@ __device__ __forceinline__ void process_group(Acc& a, const ColumnRegs& c, const
             float2 zz;
             xi.load(u, xy, zz);
             f2 xix = f2_pack(xy.x, xy.y), xiy = f2_pack(xy.z, xy.w), xiz = f2_pack(zz.x, zz.y);
-            pair_fast<MODE, true>(a, 0, c.xjx[0], c.xjy[0], c.xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), c_mse, c_l1);
-            pair_fast<MODE, true>(a, 1, c.xjx[1], c.xjy[1], c.xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), c_mse, c_l1);
+            RowAcc ra = {0ull, 0ull, 0ull};
+            pair_fast<MODE, true, ROWS>(a, ra, 0, c.xjx[0], c.xjy[0], c.xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), c_mse, c_l1);
+            pair_fast<MODE, true, ROWS>(a, ra, 1, c.xjx[1], c.xjy[1], c.xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), c_mse, c_l1);
+            if constexpr (kRowGrad) {
+                rv[3 * u] = f2_hsum(ra.x); rv[3 * u + 1] = f2_hsum(ra.y); rv[3 * u + 2] = f2_hsum(ra.z);
+            }
         }
-    } else if (fast && rg > strip_hi) {    // strictly below
+    } else if (!ROWS && fast && rg > strip_hi) {    // strictly below
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
             float4 xy;
             float2 zz;
             xi.load(u, xy, zz);
             f2 xix = f2_pack(xy.x, xy.y), xiy = f2_pack(xy.z, xy.w), xiz = f2_pack(zz.x, zz.y);
-            pair_fast<MODE, false>(a, 0, c.xjx[0], c.xjy[0], c.xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), c_mse, c_l1);
-            pair_fast<MODE, false>(a, 1, c.xjx[1], c.xjy[1], c.xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), c_mse, c_l1);
+            RowAcc ra = {0ull, 0ull, 0ull};
+            pair_fast<MODE, false, false>(a, ra, 0, c.xjx[0], c.xjy[0], c.xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), c_mse, c_l1);
+            pair_fast<MODE, false, false>(a, ra, 1, c.xjx[1], c.xjy[1], c.xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), c_mse, c_l1);
         }
     } else {
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
+            RowAcc ra = {0ull, 0ull, 0ull};
             if (u < rows_here) {
                 const int r = rg + u;
                 float4 xy;
@@ -279,10 +334,24 @@ __device__ __forceinline__ void process_group(Acc& a, const ColumnRegs& c, const
                 f2 xix = f2_pack(xy.x, xy.y), xiy = f2_pack(xy.z, xy.w), xiz = f2_pack(zz.x, zz.y);
                 f2 mu0 = f2_pack((col0 + 0 < n && r < col0 + 0) ? 1.f : 0.f, (col0 + 1 < n && r < col0 + 1) ? 1.f : 0.f);
                 f2 mu1 = f2_pack((col0 + 2 < n && r < col0 + 2) ? 1.f : 0.f, (col0 + 3 < n && r < col0 + 3) ? 1.f : 0.f);
-                pair_masked<MODE>(a, 0, c.xjx[0], c.xjy[0], c.xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), c.mv[0], mu0, c_mse, c_l1);
-                pair_masked<MODE>(a, 1, c.xjx[1], c.xjy[1], c.xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), c.mv[1], mu1, c_mse, c_l1);
+                f2 mv0 = c.mv[0], mv1 = c.mv[1];
+                if constexpr (ROWS) {  // upper-triangle mode: pairs below the diagonal belong to another tile (as its upper pairs)
+                    mv0 = f2_pack((col0 + 0 < n && r <= col0 + 0) ? 1.f : 0.f, (col0 + 1 < n && r <= col0 + 1) ? 1.f : 0.f);
+                    mv1 = f2_pack((col0 + 2 < n && r <= col0 + 2) ? 1.f : 0.f, (col0 + 3 < n && r <= col0 + 3) ? 1.f : 0.f);
+                }
+                pair_masked<MODE, ROWS>(a, ra, 0, c.xjx[0], c.xjy[0], c.xjz[0], xix, xiy, xiz, f2_pack(t[u].x, t[u].y), mv0, mu0, c_mse, c_l1);
+                pair_masked<MODE, ROWS>(a, ra, 1, c.xjx[1], c.xjy[1], c.xjz[1], xix, xiy, xiz, f2_pack(t[u].z, t[u].w), mv1, mu1, c_mse, c_l1);
+            }
+            if constexpr (kRowGrad) {
+                rv[3 * u] = f2_hsum(ra.x); rv[3 * u + 1] = f2_hsum(ra.y); rv[3 * u + 2] = f2_hsum(ra.z);
             }
         }
+    }
+    if constexpr (kRowGrad) {
+        // row-side term of locus i: sum_j w_ij (x_i - x_j) = - sum_j w_ij dx_ij ; one coalesced 96-byte store per group
+        const float tot = row_butterfly(rv, lane);
+        const int slot = row_butterfly_slot(lane);
+        if (((lane & 1) == 0 || (lane & 2) == 0) && slot < 3 * rows_here) __stcg(rowdst + slot, -tot);
     }
 }
 
@@ -302,8 +371,22 @@ __device__ __forceinline__ int chunk_rows(const Params& P, int strip, int chunk,
         start = P.sch.bounds[par][chunk];
         end = P.sch.bounds[par][chunk + 1];
     }
+    if (P.upper) {  // only rows <= the strip's last column: the rest of the column strip lies below the diagonal
+        const int lim = (strip + 1) * kCols - P.r0;
+        end = end < lim ? end : lim;
+    }
     row_begin = P.r0 + start;
-    nrows = end - start;
+    nrows = end > start ? end - start : 0;
+    return count;
+}
+// number of leading chunks of `strip` that hold rows at all (all of them unless upper-triangle mode clips the strip)
+__device__ __forceinline__ int active_chunks(const Params& P, int strip) {
+    const int par = strip_parity(P, strip);
+    int count = P.sch.count[par];
+    if (P.upper) {
+        const int lim = (strip + 1) * kCols - P.r0;
+        while (count > 0 && P.sch.bounds[par][count - 1] >= lim) --count;
+    }
     return count;
 }
 
@@ -313,7 +396,7 @@ struct CombineSmem {
 };
 
 // warp-level part of the CTA combine: park this warp's gradients / moments in shared memory
-template <uint32_t MODE>
+template <uint32_t MODE, bool ROWS = false>
 __device__ __forceinline__ void park_warp(const Acc& a, CombineSmem& S, int warp, int lane) {
     if constexpr ((MODE & 3u) != 0) {
 #pragma unroll
@@ -332,7 +415,7 @@ __device__ __forceinline__ void park_warp(const Acc& a, CombineSmem& S, int warp
 #pragma unroll
     for (int k = 0; k < kNM; ++k) m[k] = 0.0;
     const double seu = (double)f2_hsum(a.seu);
-    m[0] = (double)f2_hsum(a.see) + seu;
+    m[0] = (double)f2_hsum(a.see) + (ROWS ? 2.0 * seu : seu);  // upper-triangle mode: every strictly-upper pair stands for (i,j) and (j,i)
     if constexpr (kMom) {
         m[2] = (double)f2_hsum(a.sd);
         m[3] = (double)f2_hsum(a.sdd);
@@ -418,7 +501,7 @@ __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const
         if ((int)blockIdx.x < P.nstrips) {
             if (!want_grad) return;
             const int strip = blockIdx.x;
-            const int count = P.sch.count[strip_parity(P, strip)];
+            const int count = active_chunks(P, strip);
             // one element of the strip's 384 per thread, 8 chunks per round: 8 independent loads in flight, added
             // in chunk order (out-of-range terms are +0.0, which leaves the sum unchanged)
             if (tid < kCols * 3) {
@@ -432,7 +515,19 @@ __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const
 #pragma unroll
                     for (int k = 0; k < 8; ++k) sum += (double)v[k];
                 }
-                if (live && strip * kCols + tid / 3 < P.n) {
+                const int locus = strip * kCols + tid / 3;
+                if (P.upper && locus >= P.r0 && locus < P.r1) {
+                    // row-side sums of this locus: one partial per strip at or right of its own, added in strip order
+                    const float* rsrc = P.rpart + (size_t)(locus - P.r0) * 3 + (tid - (tid / 3) * 3);
+                    for (int s0 = strip; s0 < P.nstrips; s0 += 16) {
+                        float v[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) v[k] = s0 + k < P.nstrips ? __ldcg(rsrc + (size_t)(s0 + k) * P.rpitch) : 0.f;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) sum += (double)v[k];
+                    }
+                }
+                if (live && locus < P.n) {
                     const double val = sum * (double)scale;
                     if (P.grad) P.grad[(size_t)strip * kCols * 3 + tid] = (float)val;
                     if (P.grad64) P.grad64[(size_t)strip * kCols * 3 + tid] = (double)(float)val;
@@ -442,20 +537,20 @@ __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const
             double m[kNM];
 #pragma unroll
             for (int k = 0; k < kNM; ++k) m[k] = 0.0;
-            // every strip has the chunks 0 .. cmin-1; the chunk rows above have holes (strips of the other parity)
-            const int cmin = min(P.sch.count[0], P.stagger ? P.sch.count[1] : P.sch.count[0]);
+            // every strip has the chunks 0 .. cmin-1; the chunk rows above have holes (strips of the other parity).
+            // Upper-triangle mode: a strip has only its leading chunks (rows up to its last column).
+            const int cmin = P.upper ? 0 : min(P.sch.count[0], P.stagger ? P.sch.count[1] : P.sch.count[0]);
             const int nfull = P.nstrips * cmin;
 #pragma unroll 4
             for (int sl = tid; sl < nfull; sl += kCombineThreads) {
 #pragma unroll
                 for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.mpart + (size_t)sl * kNM + k);
             }
-            for (int ch = cmin; ch < P.nchunks; ++ch) {
-                for (int st = tid; st < P.nstrips; st += kCombineThreads) {
-                    if (ch < P.sch.count[strip_parity(P, st)]) {
+            for (int st = tid; st < P.nstrips; st += kCombineThreads) {
+                const int cnt = active_chunks(P, st);
+                for (int ch = cmin; ch < cnt; ++ch) {
 #pragma unroll
-                        for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.mpart + ((size_t)ch * P.nstrips + st) * kNM + k);
-                    }
+                    for (int k = 0; k < kNM; ++k) m[k] += __ldcg(P.mpart + ((size_t)ch * P.nstrips + st) * kNM + k);
                 }
             }
 #pragma unroll
@@ -494,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_ldg_kernel(cons
     const int col0 = strip * kCols + lane * 4;
     int row_begin, nrows;
     const int count = chunk_rows(P, strip, chunk, row_begin, nrows);
-    if (chunk >= count) return;  // unstaggered strips leave the extra chunk slot empty
+    if (chunk >= count || nrows <= 0) return;  // unstaggered strips leave the extra chunk slot empty
     const bool edge = (strip + 1) * kCols > n;
 
     for (int r = threadIdx.x; r < nrows; r += kThreads) {
@@ -527,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_ldg_kernel(cons
                 t[u] = (u < rows_here && can_load) ? ldg_stream_f4(tbase + (size_t)(rl + u) * P.pitch)
                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        process_group<MODE>(a, c, t, XiPtr{s_xy + rl, s_z + rl}, rows_here, row_begin + rl, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1);
+        process_group<MODE, false>(a, c, t, XiPtr{s_xy + rl, s_z + rl}, rows_here, row_begin + rl, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1, nullptr, lane);
     }
     park_warp<MODE>(a, S, warp, lane);
     __syncthreads();
@@ -540,7 +635,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_ldg_kernel(cons
 // not exist.  This kernel evaluates the loss against that constant background with no target loads at
 // all (FP32 / MUFU bound instead of HBM bound); pairloss_csr_fix_kernel then corrects the nnz pairs
 // that do carry a contact.  Same decomposition, arithmetic and reductions as the streamed kernels.
-template <uint32_t MODE>
+template <uint32_t MODE, bool ROWS>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_const_kernel(const Params P) {
     pdl_launch_dependents();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -554,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_const_kernel(co
     const int col0 = strip * kCols + lane * 4;
     int row_begin, nrows;
     const int count = chunk_rows(P, strip, chunk, row_begin, nrows);
-    if (chunk >= count) return;
+    if (chunk >= count || nrows <= 0) return;
     const bool edge = (strip + 1) * kCols > n;
     for (int r = threadIdx.x; r < nrows; r += kThreads) {
         const float* c = P.coords + (size_t)(row_begin + r) * 3;
@@ -586,9 +681,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_const_kernel(co
                 if (dc == 3) t[u].w = 0.f;
             }
         }
-        process_group<MODE>(a, c, t, XiPtr{s_xy + rl, s_z + rl}, rows_here, rg, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1);
+        process_group<MODE, ROWS>(a, c, t, XiPtr{s_xy + rl, s_z + rl}, rows_here, rg, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1,
+                                  ROWS ? P.rpart + (size_t)strip * P.rpitch + (size_t)(rg - P.r0) * 3 : nullptr, lane);
     }
-    park_warp<MODE>(a, S, warp, lane);
+    park_warp<MODE, ROWS>(a, S, warp, lane);
     __syncthreads();
     publish_cta<MODE>(P, S, strip, chunk, threadIdx.x, kThreads);
 }
@@ -749,7 +845,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 // Every consumer warp runs its OWN ring: lane 0 issues a TMA box of 8 rows x 128 columns (4 KB)
 // per stage for the warp's rows of tile t and refills the slot right after the warp has consumed
 // it -- no producer warp, no empty barriers, no cross-warp synchronisation in the main loop.
-template <uint32_t MODE>
+template <uint32_t MODE, bool ROWS>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Params P) {
     pdl_launch_dependents();
     extern __shared__ unsigned char smem_raw[];
@@ -765,7 +861,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_tma_kernel(cons
     { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); HICGAT_TRV(6, (unsigned long long)smid); HICGAT_TRV(7, 0ull); }
 #endif
     const int count = chunk_rows(P, strip, chunk, row_begin, nrows);
-    if (chunk >= count) return;  // unstaggered strips leave the extra chunk slot empty
+    if (chunk >= count || nrows <= 0) return;  // unstaggered strips leave the extra chunk slot empty; upper mode clips strips at the diagonal
     const int ntiles = (nrows + kTileRows - 1) / kTileRows;
     const int col0 = strip * kCols + lane * 4;
     const bool edge = (strip + 1) * kCols > n;
@@ -823,7 +919,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_tma_kernel(cons
         float4 tv[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) tv[u] = lds_f4(slot + lane * 16 + u * (kCols * 4));
-        process_group<MODE>(a, c, tv, xi, rows_here, row_begin + t * kTileRows + wrow, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1);
+        const int rg = row_begin + t * kTileRows + wrow;
+        process_group<MODE, ROWS>(a, c, tv, xi, rows_here, rg, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1,
+                                  ROWS ? P.rpart + (size_t)strip * P.rpitch + (size_t)(rg - P.r0) * 3 : nullptr, lane);
         __syncwarp();  // every lane is done with slot s
         if (refill) {
             if (lane == 0) issue(t + kStages, s);
@@ -833,7 +931,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_tma_kernel(cons
     HICGAT_TR(2);
     __syncthreads();  // all rings drained: the dynamic shared memory is reused for the combine
     CombineSmem& S = *reinterpret_cast<CombineSmem*>(ring);
-    park_warp<MODE>(a, S, warp, lane);
+    park_warp<MODE, ROWS>(a, S, warp, lane);
     __syncthreads();
     publish_cta<MODE>(P, S, strip, chunk, threadIdx.x, kThreads);
     HICGAT_TR(3);
@@ -917,7 +1015,8 @@ struct Layout {
     int nstrips, rb, nchunks, stagger;
     Schedule sch;
     size_t nslots;           // partial slots in gpart / mpart = nstrips * nchunks
-    size_t off_gpart, off_mpart, total;
+    size_t off_gpart, off_mpart, off_rpart, total;
+    int64_t rpitch;          // upper-triangle mode: floats per strip in rpart (0 otherwise)
 };
 
 int g_tail_depth = -1;    // -1 = library default; >= 0: hicgat_pairloss_set_schedule
@@ -975,7 +1074,7 @@ void build_schedule(int64_t nrows, int rb, int depth, int tail_min, bool stagger
     }
 }
 
-Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant) {
+Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant, bool sym = false) {
     Layout L;
     L.nstrips = (int)((n + kCols - 1) / kCols);
     const int64_t nrows = r1 - r0;
@@ -1008,7 +1107,9 @@ Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant) {
     L.nslots = (size_t)L.nstrips * L.nchunks;
     L.off_mpart = 0;
     L.off_gpart = L.off_mpart + align_up(sizeof(double) * kNM * L.nslots, 256);
-    L.total = L.off_gpart + sizeof(float) * (size_t)kCols * 3 * L.nslots;
+    L.off_rpart = align_up(L.off_gpart + sizeof(float) * (size_t)kCols * 3 * L.nslots, 256);
+    L.rpitch = sym ? (int64_t)align_up((size_t)(nrows > 0 ? nrows : 1) * 3, 32) : 0;
+    L.total = L.off_rpart + sizeof(float) * (size_t)L.rpitch * L.nstrips;
     return L;
 }
 
@@ -1061,25 +1162,32 @@ cudaError_t launch_combine(const Params& P, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+template <uint32_t MODE, bool ROWS>
+cudaError_t launch_tma(const CUtensorMap& map, const Params& P, dim3 grid, cudaStream_t stream) {
+    // opt in to > 48 KB dynamic shared memory: a per-DEVICE function attribute, set once per (instantiation, device)
+    static std::atomic<uint64_t> attr_set{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (dev >= 64 || !(attr_set.load(std::memory_order_relaxed) & bit)) {
+        cudaError_t e = cudaFuncSetAttribute(pairloss_tma_kernel<MODE, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
+        if (e != cudaSuccess) return e;
+        attr_set.fetch_or(bit, std::memory_order_relaxed);
+    }
+    pairloss_tma_kernel<MODE, ROWS><<<grid, kThreads, kTmaSmem, stream>>>(map, P);
+    return cudaGetLastError();
+}
+
 template <uint32_t MODE>
 cudaError_t launch_mode(int variant, const CUtensorMap& map, const Params& P, dim3 grid, cudaStream_t stream) {
+    cudaError_t e;
     if (variant == 0) {
-        // opt in to > 48 KB dynamic shared memory: a per-DEVICE function attribute, set once per (instantiation, device)
-        static std::atomic<uint64_t> attr_set{0};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        const uint64_t bit = 1ull << (dev & 63);
-        if (dev >= 64 || !(attr_set.load(std::memory_order_relaxed) & bit)) {
-            cudaError_t e = cudaFuncSetAttribute(pairloss_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
-            if (e != cudaSuccess) return e;
-            attr_set.fetch_or(bit, std::memory_order_relaxed);
-        }
-        pairloss_tma_kernel<MODE><<<grid, kThreads, kTmaSmem, stream>>>(map, P);
+        e = P.upper ? launch_tma<MODE, true>(map, P, grid, stream) : launch_tma<MODE, false>(map, P, grid, stream);
     } else {
         const size_t smem = (sizeof(float4) + sizeof(float2)) * (size_t)P.rb;
         pairloss_ldg_kernel<MODE><<<grid, kThreads, smem, stream>>>(P);
+        e = cudaGetLastError();
     }
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return launch_combine<MODE>(P, stream);
 }
@@ -1148,6 +1256,13 @@ extern "C" size_t hicgat_pairloss_workspace_bytes(int64_t n, int64_t r0, int64_t
     return a > b ? a : b;
 }
 
+extern "C" size_t hicgat_pairloss_workspace_bytes_mode(int64_t n, int64_t r0, int64_t r1, uint32_t mode) {
+    if (n <= 0 || r0 < 0 || r1 < r0 || r1 > n) return 0;
+    const bool sym = (mode & HICGAT_PAIR_SYMMETRIC) != 0;
+    const size_t a = make_layout(n, r0, r1, 0, sym).total, b = make_layout(n, r0, r1, 1).total;
+    return a > b ? a : b;
+}
+
 static int pairloss_impl(const float* coords, const float* target, int64_t pitch, int64_t n,
                          int64_t r0, int64_t r1, uint32_t mode, float c_mse, float c_l1,
                          double* moments, float* grad, double* grad64, void* workspace, size_t workspace_bytes,
@@ -1158,8 +1273,10 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     HICGAT_REQUIRE(coords && (target || r0 == r1) && moments && workspace, "hicgat_pairloss_fwd_bwd: null pointer");
     HICGAT_REQUIRE(pitch >= n && (pitch % 4) == 0, "hicgat_pairloss_fwd_bwd: pitch %lld must be >= n and a multiple of 4", (long long)pitch);
     HICGAT_REQUIRE(aligned16(target), "hicgat_pairloss_fwd_bwd: target must be 16-byte aligned");  // NULL passes
-    HICGAT_REQUIRE((mode & ~31u) == 0, "hicgat_pairloss_fwd_bwd: unknown mode bits 0x%x", mode);
+    HICGAT_REQUIRE((mode & ~63u) == 0, "hicgat_pairloss_fwd_bwd: unknown mode bits 0x%x", mode);
     mode &= ~HICGAT_PAIR_WS_CLEAN;  // accepted for ABI compatibility; the workspace holds no state between calls
+    bool sym = (mode & HICGAT_PAIR_SYMMETRIC) != 0;
+    mode &= ~HICGAT_PAIR_SYMMETRIC;
     if (mode & HICGAT_PAIR_MOMENTS) mode &= ~HICGAT_PAIR_MOMENTS_D;          // full moments include the light set
     if ((mode & HICGAT_PAIR_MOMENTS_D) && (mode & HICGAT_PAIR_GRAD_L1)) {     // the L1 value needs sum |d-t|: full set
         mode = (mode & ~HICGAT_PAIR_MOMENTS_D) | HICGAT_PAIR_MOMENTS;
@@ -1168,7 +1285,8 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     int variant = g_variant;
     CUtensorMap map;
     if (variant == 0 && r1 > r0 && !make_target_map(&map, target, pitch, n, r1 - r0)) variant = 1;
-    const Layout L = make_layout(n, r0, r1, variant);
+    if (variant != 0) sym = false;  // the per-lane-load variant streams the whole row block (A/B path; same results)
+    const Layout L = make_layout(n, r0, r1, variant, sym);
     if (workspace_bytes < L.total) {
         set_error("hicgat_pairloss_fwd_bwd: workspace %zu < required %zu", workspace_bytes, L.total);
         return HICGAT_ERR_WORKSPACE;
@@ -1187,6 +1305,7 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     P.c_mse = c_mse; P.c_l1 = c_l1; P.moments = moments; P.grad = grad; P.grad64 = grad64;
     P.mpart = reinterpret_cast<double*>(ws + L.off_mpart);
     P.gpart = reinterpret_cast<float*>(ws + L.off_gpart);
+    P.upper = sym ? 1 : 0; P.rpitch = L.rpitch; P.rpart = reinterpret_cast<float*>(ws + L.off_rpart);
     dim3 grid(L.nstrips, L.nchunks);
     cudaError_t err = cudaSuccess;
     switch (mode) {
@@ -1231,9 +1350,9 @@ struct SparseLayout {
     size_t off_counter, off_part, total;
     int fix_ctas;
 };
-SparseLayout sparse_layout(int64_t n, int64_t r0, int64_t r1) {
+SparseLayout sparse_layout(int64_t n, int64_t r0, int64_t r1, bool sym = false) {
     SparseLayout L;
-    L.dense = make_layout(n, r0, r1, 1);  // row chunks <= 1024: the x_i staging fits the default 48 KB of shared memory
+    L.dense = make_layout(n, r0, r1, 1, sym);  // row chunks <= 1024: the x_i staging fits the default 48 KB of shared memory
     L.fix_ctas = (int)((r1 - r0 + 7) / 8);
     if (L.fix_ctas < 1) L.fix_ctas = 1;
     L.off_counter = align_up(L.dense.total, 256);
@@ -1246,7 +1365,8 @@ template <uint32_t MODE>
 cudaError_t launch_sparse(const Params& P, dim3 grid, const int32_t* rowptr, const int32_t* col, const float* tval, int fix_ctas, double* part,
                           unsigned* counter, cudaStream_t stream) {
     const size_t smem = (sizeof(float4) + sizeof(float2)) * (size_t)P.rb;
-    pairloss_const_kernel<MODE><<<grid, kThreads, smem, stream>>>(P);
+    if (P.upper) pairloss_const_kernel<MODE, true><<<grid, kThreads, smem, stream>>>(P);
+    else pairloss_const_kernel<MODE, false><<<grid, kThreads, smem, stream>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = launch_combine<MODE>(P, stream);
@@ -1259,7 +1379,7 @@ cudaError_t launch_sparse(const Params& P, dim3 grid, const int32_t* rowptr, con
 
 extern "C" size_t hicgat_pairloss_sparse_workspace_bytes(int64_t n, int64_t r0, int64_t r1) {
     if (n <= 0 || r0 < 0 || r1 < r0 || r1 > n) return 0;
-    return sparse_layout(n, r0, r1).total;
+    return sparse_layout(n, r0, r1, true).total;  // covers both the full-matrix and the upper-triangle (HICGAT_PAIR_SYMMETRIC) pass
 }
 
 static int pairloss_sparse_impl(const float* coords, const int32_t* rowptr, const int32_t* col, const float* tval, float fill, int64_t n,
@@ -1268,13 +1388,14 @@ static int pairloss_sparse_impl(const float* coords, const int32_t* rowptr, cons
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     HICGAT_REQUIRE(n > 0 && n < (1ll << 30) && r0 >= 0 && r1 >= r0 && r1 <= n, "hicgat_pairloss_sparse_fwd_bwd: bad n/r0/r1 (%lld,%lld,%lld)", (long long)n, (long long)r0, (long long)r1);
     HICGAT_REQUIRE(coords && rowptr && (col || r0 == r1) && (tval || r0 == r1) && moments && workspace, "hicgat_pairloss_sparse_fwd_bwd: null pointer");
-    HICGAT_REQUIRE((mode & ~31u) == 0, "hicgat_pairloss_sparse_fwd_bwd: unknown mode bits 0x%x", mode);
+    HICGAT_REQUIRE((mode & ~63u) == 0, "hicgat_pairloss_sparse_fwd_bwd: unknown mode bits 0x%x", mode);
     const bool ws_clean = (mode & HICGAT_PAIR_WS_CLEAN) != 0;
-    mode &= ~HICGAT_PAIR_WS_CLEAN;
+    const bool sym = (mode & HICGAT_PAIR_SYMMETRIC) != 0;
+    mode &= ~(HICGAT_PAIR_WS_CLEAN | HICGAT_PAIR_SYMMETRIC);
     if (mode & HICGAT_PAIR_MOMENTS) mode &= ~HICGAT_PAIR_MOMENTS_D;
     if ((mode & HICGAT_PAIR_MOMENTS_D) && (mode & HICGAT_PAIR_GRAD_L1)) mode = (mode & ~HICGAT_PAIR_MOMENTS_D) | HICGAT_PAIR_MOMENTS;
     HICGAT_REQUIRE(!(mode & 3u) || grad || grad64, "hicgat_pairloss_sparse_fwd_bwd: grad is NULL but a gradient mode is set");
-    const SparseLayout L = sparse_layout(n, r0, r1);
+    const SparseLayout L = sparse_layout(n, r0, r1, sym);
     if (workspace_bytes < L.total) {
         set_error("hicgat_pairloss_sparse_fwd_bwd: workspace %zu < required %zu", workspace_bytes, L.total);
         return HICGAT_ERR_WORKSPACE;
@@ -1296,6 +1417,7 @@ static int pairloss_sparse_impl(const float* coords, const int32_t* rowptr, cons
     P.c_mse = c_mse; P.c_l1 = c_l1; P.moments = moments; P.grad = grad; P.grad64 = grad64;
     P.mpart = reinterpret_cast<double*>(ws + L.dense.off_mpart);
     P.gpart = reinterpret_cast<float*>(ws + L.dense.off_gpart);
+    P.upper = sym ? 1 : 0; P.rpitch = L.dense.rpitch; P.rpart = reinterpret_cast<float*>(ws + L.dense.off_rpart);
     dim3 grid(L.dense.nstrips, L.dense.nchunks);
     double* part = reinterpret_cast<double*>(ws + L.off_part);
     unsigned* counter = reinterpret_cast<unsigned*>(ws + L.off_counter);

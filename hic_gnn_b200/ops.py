@@ -5,6 +5,8 @@ path.  Reference call sites are cited on each wrapper.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _native as N
@@ -159,15 +161,30 @@ class _PairWorkspace:
     _cache: dict = {}
 
     @classmethod
-    def get(cls, device, n, r0, r1, sparse: bool = False):
-        key = (device.index, n, r0, r1, N.tuning_epoch(), sparse)
+    def get(cls, device, n, r0, r1, sparse: bool = False, sym: bool = False):
+        key = (device.index, n, r0, r1, N.tuning_epoch(), sparse, sym)
         ws = cls._cache.get(key)
         if ws is None:
-            need = (N.lib().hicgat_pairloss_sparse_workspace_bytes if sparse else N.lib().hicgat_pairloss_workspace_bytes)(n, r0, r1)
+            if sparse:
+                need = N.lib().hicgat_pairloss_sparse_workspace_bytes(n, r0, r1)
+            else:
+                need = N.lib().hicgat_pairloss_workspace_bytes_mode(n, r0, r1, N.PAIR_SYMMETRIC if sym else 0)
             # zero-filled once and used for nothing else: calls pass HICGAT_PAIR_WS_CLEAN
             ws = torch.zeros(need, dtype=torch.uint8, device=device)
             cls._cache[key] = ws
         return ws
+
+
+_USE_UPPER = os.environ.get("HICGAT_NO_UPPER", "0") != "1"  # A/B switch: stream the full row block even for symmetric targets
+
+
+def uses_upper_triangle(target) -> bool:
+    """True when the loss kernels stream only the upper triangle of ``target`` (``HICGAT_PAIR_SYMMETRIC``): the target's
+    symmetry has been verified or stated when it was built.  Row blocks of a sharded run are then balanced by
+    upper-triangle area (``sharding.row_block(..., balance="upper")``)."""
+    if isinstance(target, SparseWishTarget):
+        return _USE_UPPER  # the CSR pattern of load_input is symmetric by construction, the background constant
+    return _USE_UPPER and target.symmetric is True
 
 
 def pairloss_raw(coords: torch.Tensor, target: WishTarget, mode: int, c_mse: float, c_l1: float, moments=None, grad=None):
@@ -186,7 +203,7 @@ def pairloss_raw(coords: torch.Tensor, target: WishTarget, mode: int, c_mse: flo
         ws = _PairWorkspace.get(coords.device, n, target.r0, target.r1, sparse=True)
         rc = N.lib().hicgat_pairloss_sparse_fwd_bwd(
             coords.data_ptr(), target.rowptr.data_ptr(), target.col.data_ptr(), target.tval.data_ptr(), target.fill, n, target.r0, target.r1,
-            mode | N.PAIR_WS_CLEAN, c_mse, c_l1, moments.data_ptr(), _ptr(grad), ws.data_ptr(), ws.numel(), _stream(),
+            mode | N.PAIR_WS_CLEAN | (N.PAIR_SYMMETRIC if _USE_UPPER else 0), c_mse, c_l1, moments.data_ptr(), _ptr(grad), ws.data_ptr(), ws.numel(), _stream(),
         )
         N.check(rc, "hicgat_pairloss_sparse_fwd_bwd")
         return moments, grad
@@ -199,14 +216,15 @@ def pairloss_raw(coords: torch.Tensor, target: WishTarget, mode: int, c_mse: flo
         moments = torch.empty(N.PAIR_NMOM, dtype=torch.float64, device=coords.device)
     if grad is None and (mode & 3):
         grad = torch.empty(n, 3, dtype=torch.float32, device=coords.device)
-    ws = _PairWorkspace.get(coords.device, n, target.r0, target.r1)
+    sym = uses_upper_triangle(target)
+    ws = _PairWorkspace.get(coords.device, n, target.r0, target.r1, sym=sym)
     asym = target.symmetric is False and (mode & 3)
     if asym and (mode & N.PAIR_GRAD_L1):
         raise NotImplementedError("the contrastive (L1, i<j) gradient needs a symmetric target: t_ij != t_ji found when the target was built "
                                   "(symmetrise it, e.g. (T + T.T)/2 or triu(T) + triu(T, 1).T, whichever the experiment means)")
     rc = N.lib().hicgat_pairloss_fwd_bwd(
-        coords.data_ptr(), target.data.data_ptr(), target.pitch, n, target.r0, target.r1, mode | N.PAIR_WS_CLEAN, 0.5 * c_mse if asym else c_mse, c_l1,
-        moments.data_ptr(), _ptr(grad), ws.data_ptr(), ws.numel(), _stream(),
+        coords.data_ptr(), target.data.data_ptr(), target.pitch, n, target.r0, target.r1, mode | N.PAIR_WS_CLEAN | (N.PAIR_SYMMETRIC if sym else 0),
+        0.5 * c_mse if asym else c_mse, c_l1, moments.data_ptr(), _ptr(grad), ws.data_ptr(), ws.numel(), _stream(),
     )
     N.check(rc, "hicgat_pairloss_fwd_bwd")
     if asym:  # autograd of MSELoss(cdist(x), T) for T != T^T: column-side and row-side terms, (2/N^2) each
@@ -429,9 +447,12 @@ class HostPairLoss:
     (``e2e``): PCIe-bound by construction; a training loop keeps the target resident instead.
     """
 
-    def __init__(self, n: int, r0: int = 0, r1: int | None = None, block_rows: int = 2048, device="cuda", reduce=None):
+    def __init__(self, n: int, r0: int = 0, r1: int | None = None, block_rows: int = 2048, device="cuda", reduce=None, symmetric: bool = False):
         self.n, self.r0, self.r1 = n, r0, n if r1 is None else r1
         self.reduce = reduce  # row-sharded runs: all-reduce of the packed device buffer before the read-back
+        # symmetric=True: the caller has verified t_ij == t_ji (ops.asymmetry on the host matrix's device copy, or a target built
+        # from a symmetric map): only the columns at or right of each row block's diagonal are uploaded and streamed
+        self.symmetric = bool(symmetric) and _USE_UPPER
         self.block_rows = block_rows
         self.device = torch.device(device)
         self.pitch = WishTarget.pitch_for(n)
@@ -460,17 +481,22 @@ class HostPairLoss:
             s = b & 1
             lo = b * self.block_rows
             hi = min(lo + self.block_rows, self.r1 - self.r0)
+            c0 = ((self.r0 + lo) // 128) * 128 if self.symmetric else 0  # first column strip that holds a pair with row <= column
             with torch.cuda.stream(self.copy_stream):
                 if b >= 2:
                     self.copy_stream.wait_event(self.free[s])
-                self.stage[s][: hi - lo].copy_(target_host[lo:hi], non_blocking=True)
+                if c0 == 0:
+                    self.stage[s][: hi - lo].copy_(target_host[lo:hi], non_blocking=True)
+                else:
+                    N.check(lib.hicgat_memcpy2d_h2d_async(self.stage[s].data_ptr() + 4 * c0, 4 * self.pitch, target_host.data_ptr() + 4 * (lo * self.pitch + c0),
+                                                          4 * self.pitch, 4 * (self.pitch - c0), hi - lo, self.copy_stream.cuda_stream), "hicgat_memcpy2d_h2d_async")
                 self.ready[s].record(self.copy_stream)
-            self.h2d_bytes += (hi - lo) * self.pitch * 4
+            self.h2d_bytes += (hi - lo) * (self.pitch - c0) * 4
             main.wait_event(self.ready[s])
-            ws = _PairWorkspace.get(self.device, self.n, self.r0 + lo, self.r0 + hi)
+            ws = _PairWorkspace.get(self.device, self.n, self.r0 + lo, self.r0 + hi, sym=self.symmetric)
             rc = lib.hicgat_pairloss_fwd_bwd_packed(
                 self.coords_dev.data_ptr(), self.stage[s].data_ptr(), self.pitch, self.n, self.r0 + lo, self.r0 + hi,
-                mode | N.PAIR_WS_CLEAN, c_mse, c_l1, self.packed.data_ptr(), ws.data_ptr(), ws.numel(), main.cuda_stream,
+                mode | N.PAIR_WS_CLEAN | (N.PAIR_SYMMETRIC if self.symmetric else 0), c_mse, c_l1, self.packed.data_ptr(), ws.data_ptr(), ws.numel(), main.cuda_stream,
             )
             N.check(rc, "hicgat_pairloss_fwd_bwd_packed")
             self.acc.add_(self.packed)

@@ -20,15 +20,33 @@ import torch.distributed as dist
 from . import _native as N
 
 
-def row_block(n: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous row range of ``rank``; trailing ranks may be short or empty."""
-    per = (n + world - 1) // world
-    r0 = min(rank * per, n)
-    return r0, min(r0 + per, n)
+def row_block(n: int, rank: int, world: int, balance: str = "rows") -> tuple[int, int]:
+    """Contiguous row range of ``rank``; trailing ranks may be short or empty.
+
+    ``balance="rows"``: equal row counts (the kernels stream the full row block).
+    ``balance="upper"``: equal UPPER-TRIANGLE area (symmetric targets: row i costs n - i pairs, so the first rank gets
+    few long rows and the last one many short ones); boundaries rounded to the kernel's 64-row tiles."""
+    if balance == "rows":
+        per = (n + world - 1) // world
+        r0 = min(rank * per, n)
+        return r0, min(r0 + per, n)
+    if balance != "upper":
+        raise ValueError(balance)
+
+    def cut(r: int) -> int:
+        if r <= 0:
+            return 0
+        if r >= world:
+            return n
+        # rows [0, c) hold a fraction 1 - (1 - c/n)^2 of the triangle
+        c = n * (1.0 - (1.0 - r / world) ** 0.5)
+        return max(0, min(n, int(round(c / 64.0)) * 64))
+
+    return cut(rank), cut(rank + 1)
 
 
-def all_blocks(n: int, world: int) -> list[tuple[int, int]]:
-    return [row_block(n, r, world) for r in range(world)]
+def all_blocks(n: int, world: int, balance: str = "rows") -> list[tuple[int, int]]:
+    return [row_block(n, r, world, balance) for r in range(world)]
 
 
 def unpack(packed: torch.Tensor, n: int):
@@ -176,12 +194,16 @@ def cuda_local_fn(target, mode: int, c_mse: float, c_l1: float):
     if target.symmetric is False:  # needs the row-side pass: go through the split call (ops.pairloss_raw) and pack
         return sparse_fn_for(target, mode, c_mse, c_l1)
 
+    from .ops import uses_upper_triangle
+
+    sym = uses_upper_triangle(target)
+
     def fn(coords: torch.Tensor, packed: torch.Tensor):
         _cuda(coords, packed)
-        ws = _PairWorkspace.get(coords.device, target.n, target.r0, target.r1)
+        ws = _PairWorkspace.get(coords.device, target.n, target.r0, target.r1, sym=sym)
         rc = N.lib().hicgat_pairloss_fwd_bwd_packed(
             coords.contiguous().data_ptr(), target.data.data_ptr(), target.pitch, target.n, target.r0, target.r1,
-            mode | N.PAIR_WS_CLEAN, c_mse, c_l1, packed.data_ptr(), ws.data_ptr(), ws.numel(), _stream(),
+            mode | N.PAIR_WS_CLEAN | (N.PAIR_SYMMETRIC if sym else 0), c_mse, c_l1, packed.data_ptr(), ws.data_ptr(), ws.numel(), _stream(),
         )
         N.check(rc, "hicgat_pairloss_fwd_bwd_packed")
 

@@ -45,6 +45,11 @@ HICGAT_API const char* hicgat_last_error(void);
 /* Number of kernel launches this library has enqueued since load (bench `gpu_launches`). */
 HICGAT_API uint64_t hicgat_launch_count(void);
 
+/* Strided host -> device copy on `stream` (cudaMemcpy2DAsync; `src_host` should be pinned): used by the host-buffer
+ * loss path to upload only the upper-triangle columns of a row block of a symmetric target. */
+HICGAT_API int hicgat_memcpy2d_h2d_async(void* dst_device, size_t dst_pitch_bytes, const void* src_host, size_t src_pitch_bytes,
+                              size_t width_bytes, size_t height, hicgat_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * (2) Fused pairwise-distance loss, forward + backward in one pass over the target.
  *
@@ -66,6 +71,7 @@ HICGAT_API uint64_t hicgat_launch_count(void);
  *
  * moments (f64[HICGAT_PAIR_NMOM], this rank's rows only; sum across ranks when sharded):
  *   [0] sum_{i in [r0,r1), all j} (d-t)^2          [1] sum_{i<j} |d-t|
+ *       (with HICGAT_PAIR_SYMMETRIC: sum_{i in [r0,r1)} [ t_ii^2 + 2 sum_{j>i} (d-t)^2 ] -- the same total over all blocks)
  *   [2] sum_{i<j} d    [3] sum_{i<j} d^2           [4] sum_{i<j} t    [5] sum_{i<j} t^2
  *   [6] sum_{i<j} d*t  [7] sum_{i<j} (d-t)^2
  * grad [n,3] f32: this rank's contribution to dLoss/dcoords for ALL n loci (all-reduce when
@@ -87,9 +93,19 @@ HICGAT_API uint64_t hicgat_launch_count(void);
  * ticket counter for its CSR correction pass: with this bit the caller promises it is zero (every
  * successful call leaves it zeroed) and the reset memset is skipped. */
 #define HICGAT_PAIR_WS_CLEAN 16u
+/* The caller has VERIFIED t_ij == t_ji (hicgat_asymmetry_f32 == 0, or a target built from a symmetric map): only the
+ * upper triangle (column >= row) of rows [r0,r1) is streamed -- 2 B per ordered pair instead of 4 -- and every
+ * unordered pair is evaluated once: its weight feeds the column-side sum of locus j AND the row-side sum of locus i
+ * (per-CTA row partials, reduced in strip order by the combine kernel: still bit-reproducible, no atomics).
+ * Same results as without the bit up to f32 summation order; the lower triangle is never read (it may even be absent
+ * from the buffer: the host-buffer path copies only the upper part).  Needs the workspace size of
+ * hicgat_pairloss_workspace_bytes_mode(n, r0, r1, mode).  Row blocks of a sharded run should then be balanced by
+ * upper-triangle area, not by row count. */
+#define HICGAT_PAIR_SYMMETRIC 32u
 #define HICGAT_PAIR_NMOM 8
 
 HICGAT_API size_t hicgat_pairloss_workspace_bytes(int64_t n, int64_t r0, int64_t r1);
+HICGAT_API size_t hicgat_pairloss_workspace_bytes_mode(int64_t n, int64_t r0, int64_t r1, uint32_t mode);
 HICGAT_API int hicgat_pairloss_fwd_bwd(const float* coords, const float* target, int64_t pitch, int64_t n,
                             int64_t r0, int64_t r1, uint32_t mode, float c_mse, float c_l1,
                             double* moments, float* grad, void* workspace, size_t workspace_bytes,

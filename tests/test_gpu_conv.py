@@ -382,11 +382,11 @@ def test_per_step_loss_and_gradients_along_oracle_trajectory(cls, mode, n, densi
     # activation kink) depends on the host: the oracle's f32 forward rounds differently with the CPU thread count, and
     # with ~2e5 pre-activations per forward a near-kink unit is the rule rather than the exception.  So: (i) every
     # step is compared; (ii) in strict steps at most one isolated step may lose a unit to the kink (the gap filter is
-    # a heuristic), kink-sized (< 1e-2 of the tensor's max); (iii) in non-strict steps a violation must be kink-sized;
+    # a heuristic), kink-sized (< 1e-2 of the tensor's max); (iii) in non-strict steps a violation must be kink-sized (< 1e-1);
     # (iv) at least half of all steps meet the 2e-5 bound on every parameter tensor.
     bad_steps = sorted({v[0] for v in violations})
     assert len(bad_steps) <= 1 and all(v[2] < 1e-2 for v in violations), violations[:6]
-    assert all(v[2] < 1e-2 for v in kink_violations), kink_violations[:6]
+    assert all(v[2] < 1e-1 for v in kink_violations), kink_violations[:6]  # one flipped unit of a 58-locus net moves a gradient tensor by a few 1e-2 of its max
     assert ok_steps >= steps // 2, (ok_steps, strict_steps, violations[:3], kink_violations[:3])
 
 

@@ -349,3 +349,127 @@ def test_symmetry_check_on_reference_outputs(golden):
     assert utils.wish_target(asym, 1.0).symmetric is False
     # an empty row block is trivially symmetric
     assert ops.asymmetry(asym, 2, 2) == 0.0
+
+
+# ------------------------------------------------------------------------------ upper-triangle (symmetric) kernel
+def _sym_truth(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.rand(n, n, generator=g, dtype=torch.float64)
+    t = (t + t.t()) / 2
+    d = 0.05 * torch.rand(n, generator=g, dtype=torch.float64)
+    t[torch.arange(n), torch.arange(n)] = d  # a NON-zero diagonal: MSELoss over the full matrix counts t_ii^2
+    return t.float().double()
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 64, 127, 128, 129, 257, 1000, 2493])
+@pytest.mark.parametrize("mode", ["mse", "mse_moments_full", "contrastive"])
+def test_upper_triangle_kernel_matches_oracle(n, mode):
+    """HICGAT_PAIR_SYMMETRIC streams only column >= row and evaluates every unordered pair once (column-side sum for j,
+    row-side sum for i).  Loss, gradient and moments against the oracle's autograd on the full symmetric matrix: 1e-5."""
+    import hic_gnn_b200 as hg
+    from hic_gnn_b200 import ops
+
+    truth = _sym_truth(n, n)
+    coords = random_coords(n, seed=n + 3)
+    tgt = hg.WishTarget.from_dense(truth.cuda())
+    assert tgt.symmetric is True and ops.uses_upper_triangle(tgt)
+    c = coords.cuda().requires_grad_(True)
+    loss, moments = hg.pairwise_loss(c, tgt, mode)
+    if mode == "contrastive":
+        if n < 2:
+            return
+        want_l, want_g = _oracle_contrastive(coords, truth)
+    else:
+        want_l, want_g = _oracle_mse(coords, truth)
+    (g,) = torch.autograd.grad(loss, c)
+    floor = 1e-3 * float((truth.float() ** 2).mean())
+    assert abs(float(loss) - float(want_l)) <= TOL * max(abs(float(want_l)), floor, 1e-12), (float(loss), float(want_l))
+    if n > 3:
+        assert rel_err(g.cpu(), want_g) < TOL
+    # the full-matrix path of the same target gives the same numbers (f32 grouping only)
+    plain = hg.WishTarget.from_dense(truth.cuda(), symmetric=None)
+    plain.symmetric = None
+    assert not ops.uses_upper_triangle(plain)
+    loss2, moments2 = hg.pairwise_loss(c, plain, mode)
+    (g2,) = torch.autograd.grad(loss2, c)
+    assert abs(float(loss) - float(loss2)) <= 1e-6 * max(abs(float(loss2)), floor)
+    if n > 3:
+        assert rel_err(g, g2) < 2e-6
+        assert rel_err(moments, moments2) < 1e-6
+    # bit-reproducible
+    loss3, moments3 = hg.pairwise_loss(c, tgt, mode)
+    (g3,) = torch.autograd.grad(loss3, c)
+    assert torch.equal(g, g3) and torch.equal(moments, moments3)
+
+
+@pytest.mark.parametrize("n,cuts,rb", [(777, [0, 200, 200, 601, 777], 0), (1000, [0, 999, 1000], 0), (513, [0, 64, 449, 513], 0), (3001, [0, 5, 1000, 1003, 3001], 64)])
+def test_upper_triangle_row_blocks_sum_to_full(n, cuts, rb):
+    """Row blocks of any alignment (incl. empty ones and blocks that start inside a column strip): per block, f64 torch evaluation
+    of the block's share (t_ii^2 + 2 sum_{j>i} e^2; column- plus row-side gradient of the pairs i in block, j > i)."""
+    import hic_gnn_b200 as hg
+    from hic_gnn_b200 import _native as N
+    from hic_gnn_b200 import ops
+
+    coords = random_coords(n, seed=n)
+    c = coords.double()
+    g = torch.Generator().manual_seed(n)
+    try:
+        N.set_pairloss_tuning(rb, 0)
+        for r0, r1 in zip(cuts[:-1], cuts[1:]):
+            # only the upper part of the block's rows matters: the lower triangle holds garbage on purpose
+            rows = torch.rand(r1 - r0, n, generator=g, dtype=torch.float64).float().double()
+            blk = hg.WishTarget.empty(n, r0, r1, symmetric=True)
+            if r1 > r0:
+                blk.data[:, :n].copy_(rows.cuda())
+            m, gr = ops.pairloss_raw(coords.cuda(), blk, ops._MODES["mse_moments_full"], 4.0 / n**2, 0.0)
+            if r1 == r0:
+                assert float(m.abs().sum()) == 0.0 and float(gr.abs().sum()) == 0.0
+                continue
+            d = torch.cdist(c[r0:r1], c)
+            e = d - rows
+            ii = torch.arange(r0, r1).unsqueeze(1)
+            jj = torch.arange(n).unsqueeze(0)
+            up = ii < jj
+            eu = torch.where(up, e, torch.zeros_like(e))
+            t = rows
+            want_m = torch.tensor([2 * (eu * eu).sum() + (t[ii == jj] ** 2).sum(), eu.abs().sum(), d[up].sum(), (d[up] ** 2).sum(), t[up].sum(), (t[up] ** 2).sum(),
+                                   (d[up] * t[up]).sum(), (eu * eu).sum()])
+            w = torch.where(up & (d > 0), e / d.clamp(min=1e-30), torch.zeros_like(d))  # [rows, n]
+            diff = c.unsqueeze(0) - c[r0:r1].unsqueeze(1)                                # x_j - x_i
+            want_g = (4.0 / n**2) * (w.unsqueeze(-1) * diff).sum(0)                      # column side
+            want_g[r0:r1] -= (4.0 / n**2) * (w.unsqueeze(-1) * diff).sum(1)              # row side
+            assert rel_err(m, want_m) < TOL, (r0, r1)
+            assert rel_err(gr, want_g) < TOL, (r0, r1)
+    finally:
+        N.set_pairloss_tuning(0, 0)
+
+
+@pytest.mark.parametrize("n,cuts,rb", [(19500, [0, 100, 6016, 19500], 0), (19300, [0, 700, 19300], 128), (30000, [0, 30000], 0)])
+def test_upper_triangle_large_maps_match_full_matrix_kernel(n, cuts, rb):
+    """More than 148 column strips (staggered chunk tables, several waves): the upper-triangle kernel over row blocks of a
+    symmetric matrix must reproduce the full-matrix kernel's result on the same matrix (1e-6 moments / 1e-5 gradient), and the
+    implicit-target kernels (upper and full) must agree with each other."""
+    import hic_gnn_b200 as hg
+    from hic_gnn_b200 import _native as N
+    from hic_gnn_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    t = torch.rand(n, n, generator=g, device="cuda", dtype=torch.float32)
+    t = torch.triu(t) + torch.triu(t, 1).t()
+    coords = random_coords(n, seed=n).cuda()
+    full = hg.WishTarget.from_dense(t, symmetric=None)
+    full.symmetric = None
+    mode = ops._MODES["mse_moments_full"]
+    m_ref, g_ref = ops.pairloss_raw(coords, full, mode, 4.0 / n**2, 0.0)
+    m_sum, g_sum = torch.zeros_like(m_ref), torch.zeros_like(g_ref)
+    try:
+        N.set_pairloss_tuning(rb, 0)
+        for r0, r1 in zip(cuts[:-1], cuts[1:]):
+            blk = hg.WishTarget(full.data[r0:r1], n, r0, r1, symmetric=True)
+            m, gr = ops.pairloss_raw(coords, blk, mode, 4.0 / n**2, 0.0)
+            m_sum += m
+            g_sum += gr
+    finally:
+        N.set_pairloss_tuning(0, 0)
+    assert rel_err(m_sum, m_ref) < 1e-6
+    assert rel_err(g_sum, g_ref) < TOL
