@@ -29,6 +29,7 @@ SIGNATURES = {
     "hicgat_pairloss_set_tuning": (C.c_int, [_i32, _i32]),
     "hicgat_pairloss_set_schedule": (C.c_int, [_i32, _i32]),
     "hicgat_pairloss_describe_schedule": (C.c_int, [_i64, _i64, _i64, _p, _i32]),
+    "hicgat_pairloss_describe_schedule_mode": (C.c_int, [_i64, _i64, _i64, _u32, _p, _i32]),
     "hicgat_pairloss_sparse_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "hicgat_pairloss_sparse_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _f32, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _p, _sz, _p]),
     "hicgat_asymmetry_f32": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _p]),
@@ -36,6 +37,10 @@ SIGNATURES = {
     "hicgat_pairloss_rowside_add": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _f32, _p, _p]),
     "hicgat_allreduce_partials_p2p": (C.c_int, [_p, _p, _i32, _i32, _i64, _i64, _i32, _u32, _p, _p, _p, _p]),
     "hicgat_allreduce_partials_twoshot": (C.c_int, [_p, _p, _p, _i32, _i32, _i64, _i32, _p, _p, _p, _p]),
+    "hicgat_rank_histograms": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _f32, _f32, _i32, _p, _p, _p]),
+    "hicgat_rank_cross_sum": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _f32, _f32, _i32, _p, _p, _p, _p]),
+    "hicgat_dist_histogram": (C.c_int, [_p, _i64, _i64, _i64, _f32, _i32, _p, _p]),
+    "hicgat_edge_dist_bins": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _f32, _i32, _p, _p]),
     "hicgat_pairdist_fwd": (C.c_int, [_p, _i64, _p, _i64, _p]),
     "hicgat_pairdist_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _p]),
     "hicgat_cont2dist_max_f64": (C.c_int, [_p, _i64, _i64, _i64, _i64, _f64, _p, _p, _sz, _p]),
@@ -63,6 +68,7 @@ SIGNATURES = {
     "hicgat_ln_relu_add_bwd_workspace_bytes": (_sz, [_i64, _i32]),
     "hicgat_ln_relu_add_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "hicgat_gemv_f64": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
+    "hicgat_spmv_csr_f64": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
     "hicgat_kr_scale_round_f64": (C.c_int, [_p, _i64, _i64, _p, _p, _i64, _i32, _p]),
     "hicgat_gat_bwd_fused": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hicgat_gat_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),

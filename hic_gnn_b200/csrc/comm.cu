@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(256) allreduce_twoshot_kernel(const PeerTable2
                                                                 double* __restrict__ out_moments) {
     const int world = WORLD ? WORLD : world_rt;
     __shared__ unsigned s_ticket;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next loss kernel may set itself up behind this one
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the producer of the local partial has completed and flushed
     const uint32_t epoch = ld_relaxed_gpu_u32(state) + 1u;
     uint32_t* const sig_a = T.pad[rank] + slot_base;             // "partial of epoch e is complete", one slot per source rank

@@ -44,10 +44,31 @@ __global__ void __launch_bounds__(256) kr_scale_round_kernel(const double* __res
     }
 }
 
+// CSR counterpart of gemv_f64_kernel for the list -> graph path that never builds the dense matrix (row f-2): y = A x with
+// A given by its symmetric CSR pattern and f64 values.  One warp per row, fixed lane-strided order => reproducible.
+__global__ void __launch_bounds__(256) spmv_csr_f64_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                           const double* __restrict__ val, int n, const double* __restrict__ x, double* __restrict__ y) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int k = rowptr[i] + lane; k < rowptr[i + 1]; k += 32) s = fma(val[k], x[col[k]], s);
+    s = warp_sum(s);
+    if (lane == 0) y[i] = s;
+}
+
 }  // namespace
 }  // namespace hicgat
 
 using namespace hicgat;
+
+extern "C" int hicgat_spmv_csr_f64(const int32_t* rowptr, const int32_t* col, const double* val, int64_t n, const double* x, double* y,
+                                   hicgat_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HICGAT_REQUIRE(rowptr && x && y && n > 0 && n < (1ll << 30), "hicgat_spmv_csr_f64: bad arguments");
+    spmv_csr_f64_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(rowptr, col, val, (int)n, x, y);
+    HICGAT_CHECK_LAUNCH("spmv_csr_f64_kernel");
+    return HICGAT_OK;
+}
 
 extern "C" int hicgat_gemv_f64(const double* A, int64_t ld, int64_t n, const double* x, double* y, hicgat_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

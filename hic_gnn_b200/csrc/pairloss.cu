@@ -28,6 +28,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
 
 #include "common.cuh"
 
@@ -875,6 +879,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_tma_kernel(cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
+    pdl_wait();  // everything the previous kernels of this stream wrote (coordinates, a freshly built target) is visible from here on
     __syncwarp();
 
     // x_i staging: lane k < 24 owns component k%3 of row k/3 and writes it duplicated (v,v)
@@ -1074,30 +1079,92 @@ void build_schedule(int64_t nrows, int rb, int depth, int tail_min, bool stagger
     }
 }
 
-Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant, bool sym = false) {
+// Upper-triangle mode: the work of a column strip grows with its index (strip s holds rows <= 128 s + 127 only), so the
+// rectangular wave-quantisation estimate of pick_rows_per_cta does not apply.  The grid is dispatched chunk-major /
+// strip-minor onto 296 CTA slots; this replays that greedy assignment with cost(item) = rows + 160 (per-CTA prologue and
+// combine, in row units) and returns the makespan.  Host side, a few ms at 50k loci: cached per shape by make_layout.
+double simulate_upper(int64_t r0, int nstrips, const Schedule& S, int stagger) {
+    std::vector<double> heap(kCtaSlots, 0.0);  // min-heap of slot finish times
+    auto cmp = [](double a, double b) { return a > b; };
+    const int nchunks = S.count[0] > S.count[1] ? S.count[0] : S.count[1];
+    double makespan = 0.0;
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        for (int strip = 0; strip < nstrips; ++strip) {
+            const int par = (stagger && ((strip / 148) & 1)) ? 1 : 0;
+            if (chunk >= S.count[par]) continue;
+            const int64_t start = S.bounds[par][chunk];
+            int64_t end = S.bounds[par][chunk + 1];
+            const int64_t lim = (int64_t)(strip + 1) * kCols - r0;
+            if (end > lim) end = lim;
+            if (end <= start) continue;  // exits at once
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            const double t = heap.back() + (double)(end - start) + 160.0;  // measured: ~5 us of CTA prologue + combine per item = 160 rows
+            heap.back() = t;
+            std::push_heap(heap.begin(), heap.end(), cmp);
+            if (t > makespan) makespan = t;
+        }
+    }
+    return makespan;
+}
+
+Layout make_layout_uncached(int64_t n, int64_t r0, int64_t r1, int variant, bool sym) {
     Layout L;
     L.nstrips = (int)((n + kCols - 1) / kCols);
     const int64_t nrows = r1 - r0;
-    L.rb = pick_rows_per_cta(nrows, L.nstrips, variant);
-    while ((nrows + L.rb - 1) / L.rb > kMaxChunks - 20) L.rb *= 2;  // boundary table size
-    const int uniform_chunks = (int)((nrows + L.rb - 1) / L.rb);
-    // stagger (chunk_rows): only where a second CTA slot per SM is filled in the first wave
-    L.stagger = (variant == 0 && g_stagger && L.nstrips > 148 && uniform_chunks >= 2) ? 1 : 0;
-    // Default tail: maps of up to 148 strips (no stagger, 1-3 items per CTA slot) end with three halving chunks
-    // down to 128 rows behind bulk chunks of at most 1024 rows (10k loci: 91.5 -> 85.3 us, measured with
-    // scripts/bench_pairloss_variants.py); staggered grids keep equal chunks (a tail measured +-1 % there).
+    const int unit = variant == 0 ? kTileRows : 8;
     int depth = 0, tail_min = g_tail_min_rows;
-    if (variant == 0) {
-        if (g_tail_depth >= 0) {
-            depth = g_tail_depth;
-        } else if (!L.stagger && nrows >= 2048 && g_rows_per_cta == 0) {
-            depth = 3;
-            tail_min = 128;
-            if (L.rb > 1024) L.rb = 1024;
+    memset(&L.sch, 0, sizeof(L.sch));
+    if (sym && g_rows_per_cta == 0 && g_tail_depth < 0 && nrows > 0) {
+        // equal chunks, no explicit tail (the triangle tapers by itself): pick the chunk length by simulation
+        static const int cand0[] = {256, 384, 512, 640, 768, 1024, 1280, 1536, 2048, 3072, 4096};
+        static const int cand1[] = {256, 384, 512, 768, 1024};  // the implicit-target kernel stages a chunk of x_i in 48 KB of shared memory
+        const int* cand = variant == 0 ? cand0 : cand1;
+        const int ncand = variant == 0 ? 11 : 5;
+        double best = 1e300;
+        int best_rb = cand[ncand - 1], best_stagger = 0, best_depth = 0;
+        for (int k = 0; k < ncand; ++k) {
+            const int rb = cand[k];
+            if ((nrows + rb - 1) / rb > kMaxChunks - 20) continue;
+            const int uniform_chunks = (int)((nrows + rb - 1) / rb);
+            const int stagger = (variant == 0 && g_stagger && L.nstrips > 148 && uniform_chunks >= 2) ? 1 : 0;
+            for (int d = 0; d <= (variant == 0 ? 3 : 0); ++d) {  // optionally a halving tail of d chunks (down to 128 rows) behind the bulk
+                Schedule S;
+                memset(&S, 0, sizeof(S));
+                build_schedule(nrows, rb, d, 128, stagger != 0, unit, S);
+                const double m = simulate_upper(r0, L.nstrips, S, stagger);
+                if (m < best * 0.995) {
+                    best = m;
+                    best_rb = rb;
+                    best_stagger = stagger;
+                    best_depth = d;
+                }
+            }
+        }
+        depth = best_depth;
+        tail_min = 128;
+        L.rb = best_rb;
+        while ((nrows + L.rb - 1) / L.rb > kMaxChunks - 20) L.rb *= 2;
+        L.stagger = best_stagger;
+    } else {
+        L.rb = pick_rows_per_cta(nrows, L.nstrips, variant);
+        while ((nrows + L.rb - 1) / L.rb > kMaxChunks - 20) L.rb *= 2;  // boundary table size
+        const int uniform_chunks = (int)((nrows + L.rb - 1) / L.rb);
+        // stagger (chunk_rows): only where a second CTA slot per SM is filled in the first wave
+        L.stagger = (variant == 0 && g_stagger && L.nstrips > 148 && uniform_chunks >= 2) ? 1 : 0;
+        // Default tail: maps of up to 148 strips (no stagger, 1-3 items per CTA slot) end with three halving chunks
+        // down to 128 rows behind bulk chunks of at most 1024 rows (10k loci: 91.5 -> 85.3 us, measured with
+        // scripts/bench_pairloss_variants.py); staggered grids keep equal chunks (a tail measured +-1 % there).
+        if (variant == 0) {
+            if (g_tail_depth >= 0) {
+                depth = g_tail_depth;
+            } else if (!L.stagger && nrows >= 2048 && g_rows_per_cta == 0) {
+                depth = 3;
+                tail_min = 128;
+                if (L.rb > 1024) L.rb = 1024;
+            }
         }
     }
-    memset(&L.sch, 0, sizeof(L.sch));
-    build_schedule(nrows > 0 ? nrows : 1, L.rb, depth, tail_min, L.stagger != 0, variant == 0 ? kTileRows : 8, L.sch);
+    build_schedule(nrows > 0 ? nrows : 1, L.rb, depth, tail_min, L.stagger != 0, unit, L.sch);
     L.nchunks = L.sch.count[0] > L.sch.count[1] ? L.sch.count[0] : L.sch.count[1];
     // the per-lane-load and implicit-target kernels stage one chunk of x_i in shared memory: size = longest chunk
     int longest = 0;
@@ -1110,6 +1177,28 @@ Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant, bool sym = fa
     L.off_rpart = align_up(L.off_gpart + sizeof(float) * (size_t)kCols * 3 * L.nslots, 256);
     L.rpitch = sym ? (int64_t)align_up((size_t)(nrows > 0 ? nrows : 1) * 3, 32) : 0;
     L.total = L.off_rpart + sizeof(float) * (size_t)L.rpitch * L.nstrips;
+    return L;
+}
+
+// make_layout runs on the host for every call of the loss; the upper-triangle schedule search costs milliseconds, so
+// layouts are memoised per (shape, variant, mode, tuning).  Thread-safe.
+Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant, bool sym = false) {
+    struct Key {
+        int64_t n, r0, r1;
+        int variant, sym, rows, stagger, depth, tail_min;
+        bool operator<(const Key& o) const {
+            return std::tie(n, r0, r1, variant, sym, rows, stagger, depth, tail_min) < std::tie(o.n, o.r0, o.r1, o.variant, o.sym, o.rows, o.stagger, o.depth, o.tail_min);
+        }
+    };
+    static std::mutex mu;
+    static std::map<Key, Layout> cache;
+    const Key key{n, r0, r1, variant, sym ? 1 : 0, g_rows_per_cta, g_stagger, g_tail_depth, g_tail_min_rows};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    if (cache.size() > 4096) cache.clear();  // the host-buffer path walks many row blocks: bound the memo
+    const Layout L = make_layout_uncached(n, r0, r1, variant, sym);
+    cache.emplace(key, L);
     return L;
 }
 
@@ -1174,8 +1263,19 @@ cudaError_t launch_tma(const CUtensorMap& map, const Params& P, dim3 grid, cudaS
         if (e != cudaSuccess) return e;
         attr_set.fetch_or(bit, std::memory_order_relaxed);
     }
-    pairloss_tma_kernel<MODE, ROWS><<<grid, kThreads, kTmaSmem, stream>>>(map, P);
-    return cudaGetLastError();
+    // programmatic stream serialization: the CTAs may become resident (barrier init, tensor-map prefetch, schedule lookup)
+    // while the previous kernel of the stream drains; griddepcontrol.wait precedes the first global read
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kTmaSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, pairloss_tma_kernel<MODE, ROWS>, map, P);
 }
 
 template <uint32_t MODE>
@@ -1228,12 +1328,17 @@ extern "C" int hicgat_pairloss_set_schedule(int tail_depth, int tail_min_rows) {
     return HICGAT_OK;
 }
 
+extern "C" int hicgat_pairloss_describe_schedule_mode(int64_t n, int64_t r0, int64_t r1, uint32_t mode, int32_t* out, int32_t capacity);
 extern "C" int hicgat_pairloss_describe_schedule(int64_t n, int64_t r0, int64_t r1, int32_t* out, int32_t capacity) {
+    return hicgat_pairloss_describe_schedule_mode(n, r0, r1, 0u, out, capacity);
+}
+
+extern "C" int hicgat_pairloss_describe_schedule_mode(int64_t n, int64_t r0, int64_t r1, uint32_t mode, int32_t* out, int32_t capacity) {
     if (n <= 0 || r0 < 0 || r1 < r0 || r1 > n || !out || capacity < 4) {
         set_error("hicgat_pairloss_describe_schedule: bad arguments");
         return HICGAT_ERR_INVALID;
     }
-    const Layout L = make_layout(n, r0, r1, g_variant);
+    const Layout L = make_layout(n, r0, r1, g_variant, g_variant == 0 && (mode & HICGAT_PAIR_SYMMETRIC) != 0);
     const int need = 4 + (L.sch.count[0] + 1) + (L.sch.count[1] + 1);
     if (capacity < need) {
         set_error("hicgat_pairloss_describe_schedule: capacity %d < %d", (int)capacity, need);

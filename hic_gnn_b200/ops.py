@@ -126,6 +126,15 @@ class SparseWishTarget:
         tval = (dist / dist.max()).float()
         return cls(graph.n, r32, c32, tval, 1.0, r0, r1)
 
+    @classmethod
+    def from_values(cls, graph, value64: torch.Tensor, factor: float, r0: int = 0, r1: int | None = None):
+        """Same from the f64 contact value of every stored entry (``utils.load_input_sparse``: there is no dense matrix to gather
+        from): ``(1/a)^factor / max`` in f64, cast to f32 -- the values ``cont2dist`` gives the stored pairs (utils.py:75-80)."""
+        r32, c32 = graph.i32()
+        dist = (1.0 / value64.double()) ** factor
+        tval = (dist / dist.max()).float()
+        return cls(graph.n, r32, c32, tval, 1.0, r0, r1)
+
     def rows(self, r0: int, r1: int):
         return SparseWishTarget(self.n, self.rowptr, self.col, self.tval, self.fill, r0, r1)
 

@@ -67,6 +67,94 @@ def load_input(input, features, device="cuda") -> Data:
     return Data(x=x, edge_index=CSRGraph(rowptr, col, val, adj.shape[0]), y=adj)
 
 
+@dataclass
+class SparseData:
+    """:class:`Data` of a map that was never densified (:func:`load_input_sparse`): ``y`` does not exist; ``value64`` holds the
+    f64 contact value of every stored entry of ``edge_index`` (what ``y[i, j]`` would be), ``bins`` the genomic bin ids kept."""
+
+    x: torch.Tensor
+    edge_index: CSRGraph
+    value64: torch.Tensor
+    bins: torch.Tensor
+    y: None = None
+    edge_attr: None = None
+
+
+def load_input_sparse(contacts, features=None, normalize: bool = False, device="cuda") -> SparseData:
+    """``utils.load_input`` for a 3-column ``bin_i bin_j count`` list WITHOUT the dense N x N matrix (SURVEY.md section 8 row
+    f-2): the composition ``convert_to_matrix`` (utils.py:10-26) -> [``KRnorm``, r_utils.R:1-93, if ``normalize``] -> graph half of
+    ``load_input`` (utils.py:33-71), evaluated on the records themselves.  O(E log E) device work (sort / unique / searchsorted +
+    the library's CSR kernels); the reference needs an O(E N) Python loop and 8 N^2 bytes (20 GB at 50k loci).
+
+    Same semantics, record for record: bins are compacted in sorted order; a later record overwrites an earlier one for the same
+    (i, j); ``triu(mat) + tril(mat.T, 1)`` keeps the records with i <= j (mirrored), doubles the diagonal, and DROPS records below
+    the first sub-diagonal; bins whose column is all-zero afterwards are removed; the diagonal is zeroed; an edge {i, j} exists
+    iff its value is non-zero and carries ``float32(value)`` in both directions.  Records ON the first sub-diagonal would make the
+    reference's matrix asymmetric (they are added onto the super-diagonal only): such a list is refused here -- densify it with
+    ``convert_to_matrix`` / ``load_input``, whose targets know how to handle ``T != T^T``.
+    Bit-exact with the reference's ``load_input(list, ...)`` (tests/golden/reference_golden_list.npz)."""
+    from . import kr as _kr
+
+    a = torch.as_tensor(np.asarray(contacts) if not torch.is_tensor(contacts) else contacts, dtype=torch.float64).to(device)
+    n, rowptr, row, col, val, bins = _csr_arrays_from_list(a)
+    graph = CSRGraph(rowptr, col.to(torch.int64).contiguous(), val.to(torch.float32), n)
+    if normalize:                                          # the Rscript step between the two halves (HiC_GAT_generalize_directly.py:133)
+        if n and int((rowptr[1:] == rowptr[:-1]).sum()):
+            raise RuntimeError("load_input_sparse(normalize=True): a bin is left without contacts after the diagonal is removed; KRnorm drops "
+                               "such rows (r_utils.R:3-10) -- remove them from the list")
+        r32, c32 = graph.i32()
+        val = _kr.kr_norm_csr(r32, c32, val)
+        live = val != 0                                    # entries that round to zero vanish from the graph, like in the dense path
+        if not bool(live.all()):
+            row, col, val = row[live], col[live], val[live].contiguous()
+            rowptr = torch.searchsorted(row.contiguous(), torch.arange(n + 1, device=a.device)).to(torch.int64)
+        graph = CSRGraph(rowptr, col.to(torch.int64).contiguous(), val.to(torch.float32), n)
+    x = None if features is None else torch.as_tensor(features).to(device)
+    return SparseData(x=x, edge_index=graph, value64=val, bins=bins)
+
+
+def _csr_arrays_from_list(a: torch.Tensor):
+    """Device-agnostic core of :func:`load_input_sparse` (pure torch, so the CPU suite can pin it against the reference's own
+    output): ``(n, rowptr int64[n+1], row, col, value f64[nnz], kept bin ids)`` of the symmetric, diagonal-free CSR graph."""
+    if a.dim() != 2 or a.shape[1] != 3:
+        raise ValueError("load_input_sparse expects a 3-column contact list")
+    ids = torch.unique(torch.cat((a[:, 0], a[:, 1])))
+    size = ids.numel()
+    ii = torch.searchsorted(ids, a[:, 0].contiguous())
+    jj = torch.searchsorted(ids, a[:, 1].contiguous())
+    # "last record wins" per cell (utils.py:17-20): stable sort by cell, keep the last member of every run
+    lin = ii * size + jj
+    order = torch.argsort(lin, stable=True)
+    lin_s = lin[order]
+    last = torch.ones_like(lin_s, dtype=torch.bool)
+    last[:-1] = lin_s[1:] != lin_s[:-1]
+    ci, cj, cv = ii[order][last], jj[order][last], a[:, 2][order][last]
+    if bool(((ci == cj + 1) & (cv != 0)).any()):
+        raise NotImplementedError("the list holds records on the first sub-diagonal (bin_i one bin after bin_j): the reference's "
+                                  "triu(mat) + tril(mat.T, 1) (utils.py:21) makes such a map asymmetric; use convert_to_matrix / load_input")
+    up = ci < cj                                           # i > j + 1 is dropped by tril(mat.T, 1); i == j is the (doubled) diagonal
+    ui, uj, uv = ci[up], cj[up], cv[up]
+    # all-zero columns of the symmetrised matrix (utils.py:22-24): column c is non-zero iff some upper record touching c, or its diagonal, is
+    nz = torch.zeros(size, dtype=torch.bool, device=a.device)
+    live = uv != 0
+    nz[ui[live]] = True
+    nz[uj[live]] = True
+    dg = (ci == cj) & (cv != 0)
+    nz[ci[dg]] = True
+    newid = torch.cumsum(nz, 0) - 1
+    n = int(nz.sum())
+    keep = live & nz[ui] & nz[uj]                          # edges: non-zero value (load_input: sym != 0), diagonal zeroed (utils.py:33)
+    ui, uj, uv = newid[ui[keep]], newid[uj[keep]], uv[keep]
+    # both directions, row-major sorted (SparseTensor(...).to_symmetric(), utils.py:70-71)
+    row = torch.cat((ui, uj))
+    col = torch.cat((uj, ui))
+    val = torch.cat((uv, uv))
+    order = torch.argsort(row * n + col)
+    row, col, val = row[order], col[order], val[order].contiguous()
+    rowptr = torch.searchsorted(row.contiguous(), torch.arange(n + 1, device=a.device)).to(torch.int64)
+    return n, rowptr, row, col, val, ids[nz]
+
+
 def cont2dist(adj: torch.Tensor, factor: float) -> torch.Tensor:
     """``utils.cont2dist`` (utils.py:75-80): f64 N x N wish distances on the GPU."""
     return ops.cont2dist(adj.contiguous(), factor, want_f64=True, want_f32=False)[0]
@@ -78,10 +166,12 @@ def wish_target(adj: torch.Tensor, factor: float) -> ops.WishTarget:
     return ops.cont2dist(adj.contiguous(), factor, want_f64=False, want_f32=True)[1]
 
 
-def sparse_wish_target(data: Data, factor: float) -> ops.SparseWishTarget:
+def sparse_wish_target(data, factor: float) -> ops.SparseWishTarget:
     """Implicit form of :func:`wish_target` for sparse maps (row f-4): wish distances only at the
     stored pairs of ``data.edge_index``; every other pair is 1.0, the diagonal 0.  Same loss, no N x N
-    array."""
+    array.  ``data``: a :class:`Data` (values gathered from the dense ``y``) or a :class:`SparseData` (its f64 values)."""
+    if isinstance(data, SparseData):
+        return ops.SparseWishTarget.from_values(data.edge_index, data.value64, factor)
     return ops.SparseWishTarget.from_graph(data.edge_index, data.y, factor)
 
 

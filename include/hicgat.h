@@ -130,6 +130,9 @@ HICGAT_API int hicgat_pairloss_set_schedule(int tail_depth, int tail_min_rows);
  * out = [nstrips, stagger, count0, count1, bounds0[0..count0], bounds1[0..count1]] (row offsets from r0; table 1
  * is used by the staggered strips).  Returns the number of ints written or a negative error code. */
 HICGAT_API int hicgat_pairloss_describe_schedule(int64_t n, int64_t r0, int64_t r1, int32_t* out, int32_t capacity);
+/* Same for a given mode word (HICGAT_PAIR_SYMMETRIC selects the upper-triangle schedule: equal chunks whose length is
+ * chosen by replaying the chunk-major dispatch of the triangular work onto the 296 CTA slots). */
+HICGAT_API int hicgat_pairloss_describe_schedule_mode(int64_t n, int64_t r0, int64_t r1, uint32_t mode, int32_t* out, int32_t capacity);
 
 /* ------------------------------------------------------------------------------------
  * (next row f-4) The same loss against an IMPLICIT target for sparse maps: after cont2dist every
@@ -199,6 +202,29 @@ HICGAT_API int hicgat_allreduce_partials_twoshot(const uint64_t* peer_partials_h
                                       const uint64_t* signal_pads_host, int rank, int world, int64_t n, int slot_base,
                                       uint32_t* state, const double* moment_const, double* out_moments,
                                       hicgat_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (next row f-3) dSCC at scale: Spearman correlation of the i<j wish distances and reconstructed distances
+ * (scipy.stats.spearmanr on triu_indices gathers: HiC-GNN_main.py:135-139, HiC_GAT_generalize_directly.py:210-242) without the
+ * N x N distance matrix, the index arrays or a sort.  Ranks = mid-ranks of two fine histograms (bin b of value v is
+ * floor(v * scale), clamped to [0, nbins)):
+ *   hicgat_rank_histograms   pass 1 over target rows [r0,r1): hist_d[bin(d_ij)]++, hist_t[bin(t_ij)]++ for i < j (uint64 counts,
+ *                            ADDED to the buffers: zero them first; sum over ranks when sharded)
+ *   hicgat_rank_cross_sum    pass 2: cross += sum_{i<j} rank_d[bin(d_ij)] * rank_t[bin(t_ij)]  (f64; zero it first)
+ *   hicgat_dist_histogram    pass 1 for an implicit (sparse) target: hist_d only, every pair i<j of rows [r0,r1)
+ *   hicgat_edge_dist_bins    bins[k] = bin(d_ij) for every stored CSR entry k = (i, j) with j > i of rows [r0,r1), -1 otherwise
+ * The caller turns the histograms into mid-rank tables (an O(nbins) prefix sum) and the sums into Pearson's r of the ranks
+ * (hic_gnn_b200/metrics.py).  Error against exact average ranks: at most half a bin population per rank (1/(2 nbins) relative).
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API int hicgat_rank_histograms(const float* coords, const float* target, int64_t pitch, int64_t n, int64_t r0, int64_t r1,
+                           float d_scale, float t_scale, int nbins, uint64_t* hist_d, uint64_t* hist_t, hicgat_stream_t stream);
+HICGAT_API int hicgat_rank_cross_sum(const float* coords, const float* target, int64_t pitch, int64_t n, int64_t r0, int64_t r1,
+                          float d_scale, float t_scale, int nbins, const double* rank_d, const double* rank_t, double* cross,
+                          hicgat_stream_t stream);
+HICGAT_API int hicgat_dist_histogram(const float* coords, int64_t n, int64_t r0, int64_t r1, float d_scale, int nbins, uint64_t* hist_d,
+                          hicgat_stream_t stream);
+HICGAT_API int hicgat_edge_dist_bins(const float* coords, const int32_t* rowptr, const int32_t* col, int64_t n, int64_t r0, int64_t r1,
+                          float d_scale, int nbins, int32_t* bins, hicgat_stream_t stream);
 
 /* Materialising variant kept for API parity of model.forward() (returns the N x N matrix,
  * models.py:39): dist[i,j] = |x_i - x_j|, and its backward
@@ -349,6 +375,10 @@ HICGAT_API int hicgat_gat_param_grads(int64_t n, int heads, int channels, const 
  * The Newton-CG control flow lives in hic_gnn_b200/kr.py.
  * ---------------------------------------------------------------------------------- */
 HICGAT_API int hicgat_gemv_f64(const double* A, int64_t ld, int64_t n, const double* x, double* y, hicgat_stream_t stream);
+/* y = A x for a CSR matrix with f64 values (int32 rowptr[n+1] / col[nnz]): the A %*% x of KRnorm on the graph built straight
+ * from a contact list, without the dense N x N matrix (next row f-2). */
+HICGAT_API int hicgat_spmv_csr_f64(const int32_t* rowptr, const int32_t* col, const double* val, int64_t n, const double* x, double* y,
+                        hicgat_stream_t stream);
 HICGAT_API int hicgat_kr_scale_round_f64(const double* A, int64_t ld, int64_t n, const double* x, double* out, int64_t ldo,
                               int decimals, hicgat_stream_t stream);
 
