@@ -37,12 +37,10 @@ def test_streamed_dscc_matches_scipy(n, density):
     # row blocks: histograms and cross sums add up
     import hic_gnn_b200.ops as ops
 
-    hd = None
     parts = []
     for r0, r1 in [(0, n // 3), (n // 3, n)]:
         parts.append(hg.WishTarget.from_dense(truth.cuda(), r0, r1))
-    state = {"i": 0}
-    # emulate a 2-rank all-reduce on one GPU: evaluate both blocks' contributions by calling the kernels through a shared accumulator
+    # emulate a 2-rank all-reduce on one GPU: both blocks' kernels add into shared accumulators
     from hic_gnn_b200 import _native as N
 
     c = coords.cuda().contiguous()

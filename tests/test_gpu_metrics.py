@@ -30,7 +30,7 @@ def test_dscc_and_pearson_match_scipy(n, density):
     assert np.array_equal(ranks.cpu().numpy(), rankdata(dist_truth.numpy(), method="average"))
 
 
-@pytest.mark.parametrize("cls,mode,max_steps", [("Net", "mse", 4000), ("GATNetSelectiveResidualsUpdated", "mse_pearson", 400)])
+@pytest.mark.parametrize("cls,mode,max_steps", [("Net", "mse", 4000), ("GATNetSelectiveResidualsUpdated", "mse", 4000), ("GATNetSelectiveResidualsUpdated", "mse_pearson", 400)])
 def test_final_dscc_within_1e3_of_oracle_on_chr19(golden, cls, mode, max_steps):
     """``Net`` + MSE terminates by the reference's own stop rule (abs(old - new) <= 1e-8 after
     ~120 steps): final dSCC within 1e-3.  The GAT net's MSE + Pearson total keeps moving, so both
@@ -58,6 +58,11 @@ def test_final_dscc_within_1e3_of_oracle_on_chr19(golden, cls, mode, max_steps):
 
     h_o, want, init = oracle_run(odata.x.float())
     tol = 1e-3
+    if len(h_o) < max_steps and cls != "Net":
+        # stopped by the rule, at a rounding-decided step: measure the reference's own reproducibility and use it as the floor
+        pg = torch.Generator().manual_seed(11)
+        _, other, _ = oracle_run(odata.x.float() * (1 + 1e-6 * torch.randn(n, 512, generator=pg)))
+        tol = max(1e-3, 3 * abs(other - want))
     if len(h_o) == max_steps:
         # Did not stop by the rule: after 400 steps of a chaotic, unconverged run the oracle's OWN dSCC moves
         # by ~1e-2 between equivalent runs (1e-6 input perturbation, or just another thread count), so this
