@@ -53,6 +53,11 @@ __global__ void __launch_bounds__(256) cont2dist_max_kernel(const double* __rest
                     a0 = make_double2(row0[j], 0.0);
                     a1 = make_double2(row1[j], 0.0);
                 }
+                // No contact (+0.0: ~99 % of a 50k-locus map) gives (1/0)^f = +inf, which the max ignores.  When ALL elements this
+                // warp holds are +0.0 -- everything away from the diagonal band -- the f64 division chains are skipped as a whole
+                // (a warp-uniform branch: the four divisions of the generic path keep their instruction-level parallelism).
+                const bool zero4 = (__double_as_longlong(a0.x) | __double_as_longlong(a0.y) | __double_as_longlong(a1.x) | __double_as_longlong(a1.y)) == 0ll;
+                if (factor > 0.0 && __all_sync(__activemask(), zero4)) continue;
                 max_update(m, a0.x, factor, fkind, j == i);
                 max_update(m, a1.x, factor, fkind, !two || j == i + 1);
                 if (j + 1 < n) {
@@ -92,19 +97,40 @@ __global__ void __launch_bounds__(256) cont2dist_apply_kernel(const double* __re
                                                               double factor, int fkind, const double* __restrict__ max_in,
                                                               double* __restrict__ o64, int64_t ld64, float* __restrict__ o32, int64_t p32) {
     const double mx = *max_in;
+    const bool fast_ok = factor > 0.0 && mx > 0.0 && mx < CUDART_INF;
     const int j = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     const bool vin = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(adj) & 15) == 0);
     const bool v64 = o64 && ((ld64 & 1) == 0) && ((reinterpret_cast<uintptr_t>(o64) & 15) == 0);
     const bool v32 = o32 && ((p32 & 1) == 0) && ((reinterpret_cast<uintptr_t>(o32) & 7) == 0);
-    for (int i = r0 + 2 * blockIdx.y; i < r1; i += 2 * gridDim.y) {
+    constexpr int kR = 4;  // rows per iteration: all loads are issued before the first division (64 B in flight per thread)
+    for (int i = r0 + kR * blockIdx.y; i < r1; i += kR * gridDim.y) {
+        double2 av[kR];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kR; ++u) {
+            const int r = i + u;
+            av[u] = make_double2(0.0, 0.0);
+            if (r < r1 && j + 1 < n) {
+                const double* row = adj + (size_t)(r - r0) * ld;
+                av[u] = vin ? __ldg(reinterpret_cast<const double2*>(row + j)) : make_double2(row[j], row[j + 1]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kR; ++u) {
             const int r = i + u;
             if (r >= r1) break;
             const double* row = adj + (size_t)(r - r0) * ld;
             if (j + 1 < n) {
-                const double2 a = vin ? __ldg(reinterpret_cast<const double2*>(row + j)) : make_double2(row[j], row[j + 1]);
-                const double w0 = wish_value(a.x, j == r, factor, fkind, mx), w1 = wish_value(a.y, j + 1 == r, factor, fkind, mx);
+                const double2 a = av[u];
+                // +0.0 off the diagonal: (1/0)^f = +inf -> max -> max / max = exactly 1.0 (finite non-zero max).  Warp-uniform
+                // shortcut for warps that hold nothing else: no f64 divisions, the kernel runs at HBM speed away from the band.
+                const bool zero2 = (__double_as_longlong(a.x) | __double_as_longlong(a.y)) == 0ll && j != r && j + 1 != r;
+                double w0, w1;
+                if (fast_ok && __all_sync(__activemask(), zero2)) {
+                    w0 = w1 = 1.0;
+                } else {
+                    w0 = wish_value(a.x, j == r, factor, fkind, mx);
+                    w1 = wish_value(a.y, j + 1 == r, factor, fkind, mx);
+                }
                 if (o64) {
                     double* d = o64 + (size_t)(r - r0) * ld64 + j;
                     if (v64) *reinterpret_cast<double2*>(d) = make_double2(w0, w1);
@@ -315,7 +341,7 @@ extern "C" int hicgat_cont2dist_apply_f64(const double* adj, int64_t ld, int64_t
     // ~16 CTAs per SM in total; a thread owns two columns and walks row pairs with a stride of gridDim.y
     // (a CTA per (column block, row) would be 6.4 M one-element CTAs at 50k loci)
     const int64_t xblocks = (width + 511) / 512;
-    const int64_t row_pairs = (r1 - r0 + 1) / 2;
+    const int64_t row_pairs = (r1 - r0 + 3) / 4;  // row groups of 4
     int64_t yblocks = (148 * 16 + xblocks - 1) / xblocks;
     if (yblocks > row_pairs) yblocks = row_pairs;
     if (yblocks < 1) yblocks = 1;

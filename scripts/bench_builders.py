@@ -31,10 +31,23 @@ def main():
     res = {}
     for name, n, dens in (("c3", 2493, 0.95), ("c4", 9970, 0.07), ("c5", 49850, 0.01)):
         adj = synth.synthetic_map_chunked(n, dens, device="cuda")
-        ms, (_, tgt) = timed(lambda: ops.cont2dist(adj, 1.0, want_f64=False, want_f32=True))
+        # the two kernels on pre-allocated outputs (allocating the 10 GB target inside the timed region made round 1's number
+        # allocator-dependent: 14 .. 64 ms between runs)
+        from hic_gnn_b200 import _native as N
+        lib, st = N.lib(), torch.cuda.current_stream().cuda_stream
+        mx = torch.empty(1, dtype=torch.float64, device="cuda")
+        ws = torch.empty(lib.hicgat_cont2dist_workspace_bytes(n, 0, n), dtype=torch.uint8, device="cuda")
+        tgt = ops.WishTarget.empty(n, 0, n, "cuda", True)
+        ms_max, _ = timed(lambda: N.check(lib.hicgat_cont2dist_max_f64(adj.data_ptr(), adj.stride(0), n, 0, n, 1.0, mx.data_ptr(), ws.data_ptr(), ws.numel(), st)), reps=5)
+        ms_app, _ = timed(lambda: N.check(lib.hicgat_cont2dist_apply_f64(adj.data_ptr(), adj.stride(0), n, 0, n, 1.0, mx.data_ptr(), None, n, tgt.data.data_ptr(), tgt.pitch, st)), reps=5)
+        res[f"cont2dist_max_{name}"] = {"ms": ms_max, "algorithmic_GB": n * n * 8 / 1e9, "GBps": n * n * 8 / ms_max / 1e6}
+        res[f"cont2dist_apply_f32_{name}"] = {"ms": ms_app, "algorithmic_GB": n * n * 12 / 1e9, "GBps": n * n * 12 / ms_app / 1e6}
+        ms = ms_max + ms_app
         alg = n * n * (8 * 2 + 4)  # two f64 passes over the contacts + the f32 target written
         res[f"cont2dist_f32_{name}"] = {"ms": ms, "algorithmic_GB": alg / 1e9, "GBps": alg / ms / 1e6}
-        del tgt
+        del tgt, ws
+        ms, _ = timed(lambda: ops.asymmetry(adj))  # the one-off symmetry check of the target build (one f64 pass + its transposed reads)
+        res[f"asymmetry_check_{name}"] = {"ms": ms, "algorithmic_GB": n * n * 8 / 1e9, "GBps": n * n * 8 / ms / 1e6}
         ms, (rowptr, col, val) = timed(lambda: ops.csr_from_dense(adj))
         nnz = int(col.numel())
         alg = n * n * 8 * 2 * 2 + nnz * 12  # count + fill each read A[i,:] and A[:,i]; col i64 + val f32 written

@@ -441,34 +441,78 @@ def test_free_running_trajectory_within_reference_noise_envelope(cls, mode, n, d
 
 
 # ------------------------------------------------------------------------------ BASELINE.json configs[2] size (2 493 loci, near-dense)
+def _kink_free_gat(n, density, seed=2):
+    """GATConv + inputs whose 5.9 M edge logits z_ij = a_src[j] + a_dst[i] all stay at least ~1 away from the LeakyReLU kink: with
+    random parameters a few logits ALWAYS sit within f32 rounding of 0 at this edge count, their slope (1 vs 0.2) is then decided by
+    summation order on either side, and one flipped edge moves the gradients by ~1e-4 of their max (measured: every tensor of the
+    CUDA paths AND of the f32 oracle is 1e-4..1e-3 off the f64 value for such seeds).  Construction: input feature h carries
+    +-3 per locus and is routed, alone, into channel 0 of head h, where att_l picks it up: a_src[j] = +-3 + N(0, 0.2^2), a_dst[i] =
+    N(0, 0.2^2).  Every row then mixes edges on the 0.2 slope (negative sources) with edges on the slope 1."""
+    from oracle import conv as oconv
+
+    _, x, odata, gdata = _setup(n, density, seed=seed)
+    torch.manual_seed(seed)
+    oc = oconv.GATConv(512, 256, heads=2)
+    H, C = 2, 256
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        sign = torch.where(torch.rand(n, generator=g) < 0.5, -1.0, 1.0)
+        x[:, :H] = 3.0 * sign.unsqueeze(1)
+        W = oc.lin_l.weight  # [H*C, 512]
+        W[:, :H] = 0.0
+        for h in range(H):
+            W[h * C, :] = 0.0
+            W[h * C, h] = 1.0
+        oc.bias.uniform_(-0.1, 0.1)
+        for att, special in ((oc.att_l, 1.0), (oc.att_r, 0.0)):
+            att.normal_(0.0, 1.0, generator=g)
+            xl = (x @ W.t()).view(n, H, C)
+            for h in range(H):
+                att[0, h, 0] = 0.0
+                sd = float((xl[:, h, 1:] * att[0, h, 1:]).sum(-1).std())
+                att[0, h, 1:] *= 0.2 / sd
+                att[0, h, 0] = special
+        _, al, ar = oc._project(x)
+        from oracle.graph import set_diag
+
+        gsd = set_diag(odata.edge_index)
+        gap = float((al[gsd.col] + ar[gsd.row]).abs().min())
+    assert gap > 0.5, gap
+    gdata.x = x.cuda()
+    return x, odata, gdata, oc
+
+
 def test_c3_size_gat_backward_against_oracle():
     """GATConv forward AND backward at the C3 size (2 493 loci, 95 % density, 5.9 M edges) against the oracle's masked-dense
-    formulation (the literal PyG order needs a 12 GB message tensor per intermediate), both message-passing paths.  With 5.9 M
-    LeakyReLU logits a handful sit within f32 rounding of the kink in ANY seed (expected count ~ 6e6 * 2e-7 / sigma), and each such
-    edge moves d/dx of its two rows by ~1e-4: parameter gradients (sums over all edges) must meet 2e-5, d/dx must meet 2e-5 on
-    all but 0.5 % of the rows and 1e-3 everywhere."""
+    formulation (the literal PyG order needs a 12 GB message tensor per intermediate), both message-passing paths and both CSR
+    backward variants, on kink-free inputs (see _kink_free_gat).  Yardstick: the same formulation in f64; the CUDA paths must be as
+    close to it as the f32 oracle is, floor 2e-5."""
     from hic_gnn_b200 import layers as glayers
 
     n = 2493
-    x, odata, gdata, oc = _gat_case(n, 0.95, min_kink_gap=0.0)
-    xo = x.clone().requires_grad_(True)
-    yo = oc(xo, odata.edge_index, dense=True)
+    x, odata, gdata, oc = _kink_free_gat(n, 0.95)
     w = torch.randn(n, 512, generator=torch.Generator().manual_seed(7))
-    po = [xo, oc.lin_l.weight, oc.att_l, oc.att_r, oc.bias]
-    go = torch.autograd.grad((yo * w).sum(), po)
+
+    def oracle_grads(dtype):
+        import copy
+
+        m = copy.deepcopy(oc).to(dtype)
+        xo = x.to(dtype).clone().requires_grad_(True)
+        yo = m(xo, odata.edge_index, dense=True)
+        return yo.detach(), torch.autograd.grad((yo * w.to(dtype)).sum(), [xo, m.lin_l.weight, m.att_l, m.att_r, m.bias])
+
+    y64, g64 = oracle_grads(torch.float64)
+    y32, g32 = oracle_grads(torch.float32)
     for path in ("csr", "dense"):
         gc = glayers.GATConv(512, 256, heads=2).cuda()
         gc.path = path
         gc.load_state_dict(oc.state_dict())
         xg = x.cuda().requires_grad_(True)
         yg = gc(xg, gdata.edge_index)
-        assert rel_err(yg, yo) < TOL, path
+        assert rel_err(yg, y64) < max(TOL, 1.5 * rel_err(y32, y64)), path
         gg = torch.autograd.grad((yg * w.cuda()).sum(), [xg, gc.lin_l.weight, gc.att_l, gc.att_r, gc.bias])
-        for name, a, b in zip(["W", "att_l", "att_r", "bias"], gg[1:], go[1:]):
-            assert rel_err(a, b) < 2e-5, (path, name)
-        row_err = (gg[0].cpu().double() - go[0].double()).abs().amax(dim=1) / go[0].double().abs().max()
-        assert float((row_err > 2e-5).double().mean()) < 5e-3, (path, float((row_err > 2e-5).double().mean()))
-        assert float(row_err.max()) < 1e-3, (path, float(row_err.max()))
+        for name, a, b, b32 in zip(["x", "W", "att_l", "att_r", "bias"], gg, g64, g32):
+            assert rel_err(a, b) < max(2e-5, 1.5 * rel_err(b32, b)), (path, name, rel_err(a, b), rel_err(b32, b))
 
 
 def test_c3_size_full_train_step_against_oracle():
