@@ -83,6 +83,7 @@ def parse_args():
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "p2p_oneshot", "nccl"], help="exchange of the sharded loss partials")
     ap.add_argument("--emulate-world", type=int, default=0, help="profiling aid: on ONE GPU run one rank's row block of a W-way split (not a bench line)")
     ap.add_argument("--emulate-rank", type=int, default=0, help="which rank's block --emulate-world runs")
+    ap.add_argument("--no-rebalance", action="store_true", help="multi-GPU: keep the area-balanced row blocks (skip the measured rebalancing at setup)")
     ap.add_argument("--no-measure-copy", dest="measure_copy", action="store_false", help="skip the same-process copy-bandwidth control")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the training step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-sparse", action="store_true", help="skip the implicit-target (row f-4) leg")
@@ -524,11 +525,42 @@ def build_inputs(env: Env, name: str, want_graph: bool, want_cpu_rows: int):
     else:
         adj = synth.synthetic_map_chunked(n, w["density"], device=dev)
     balance = "upper" if ops._USE_UPPER else "rows"  # symmetric targets stream only the upper triangle: balance the blocks by its area
-    r0, r1 = sharding.row_block(n, env.rank, env.world, balance)
-    if env.args.emulate_world and env.world == 1:
-        r0, r1 = sharding.row_block(n, env.args.emulate_rank, env.args.emulate_world, balance)
-    # the maps are symmetric by construction (synth) / checked by the tests (fixtures): stated, not re-checked per rank
-    _, target = ops.cont2dist(adj[r0:r1], w["factor"], want_f64=False, want_f32=True, r0=r0, r1=r1, max_reduce=sharding.allreduce_max_, symmetric=True)
+    world_eff, rank_eff = (env.args.emulate_world, env.args.emulate_rank) if (env.args.emulate_world and env.world == 1) else (env.world, env.rank)
+    cuts = [sharding.row_block(n, r, world_eff, balance)[0] for r in range(world_eff)] + [n]
+    rebalanced = []
+
+    def build_target(r0, r1):
+        # the maps are symmetric by construction (synth) / checked by the tests (fixtures): stated, not re-checked per rank
+        return ops.cont2dist(adj[r0:r1], w["factor"], want_f64=False, want_f32=True, r0=r0, r1=r1, max_reduce=sharding.allreduce_max_, symmetric=True)[1]
+
+    r0, r1 = cuts[rank_eff], cuts[rank_eff + 1]
+    target = build_target(r0, r1)
+    if balance == "upper" and env.world > 1 and n >= 4096 and not env.args.no_rebalance:
+        # MEASURED load balancing (setup, outside every timed region): equal-area blocks do not take equal time, and the exchange waits
+        # for the slowest rank.  Two rounds of: time this rank's kernel, all-gather the times, move the cuts (sharding.rebalance_cuts).
+        g = torch.Generator().manual_seed(7)
+        c_probe = (0.3 * torch.randn(n, 3, generator=g)).to(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            for _w in range(3):
+                ops.pairloss_raw(c_probe, target, ops._MODES["mse"], 4.0 / n**2, 0.0)
+            env.barrier()
+            e0.record()
+            for _w in range(10):
+                ops.pairloss_raw(c_probe, target, ops._MODES["mse"], 4.0 / n**2, 0.0)
+            e1.record()
+            e1.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+            times = [torch.zeros_like(t) for _ in range(env.world)]
+            env.dist.all_gather(times, t)
+            times = [float(x) for x in times]
+            rebalanced.append({"cuts": list(cuts), "kernel_ms": [round(x, 4) for x in times]})
+            cuts = sharding.rebalance_cuts(n, cuts, times)
+            r0, r1 = cuts[rank_eff], cuts[rank_eff + 1]
+            del target
+            torch.cuda.empty_cache()
+            target = build_target(r0, r1)
+        del c_probe
     graph = None
     if want_graph:
         rowptr, col, val = ops.csr_from_dense(adj)
@@ -549,7 +581,7 @@ def build_inputs(env: Env, name: str, want_graph: bool, want_cpu_rows: int):
         out["cpu_truth"] = cpu_truth.cpu()
         if n <= 3000:
             out["adj_cpu"] = adj.cpu().numpy()
-    out.update({"adj": adj, "target": target, "graph": graph, "r0": r0, "r1": r1, "balance": balance})
+    out.update({"adj": adj, "target": target, "graph": graph, "r0": r0, "r1": r1, "balance": balance + ("+measured" if rebalanced else ""), "rebalance": rebalanced, "cuts": cuts})
     return out
 
 
@@ -593,24 +625,39 @@ def measure_workload(env: Env, name: str, primary: bool):
     barrier, max_over_ranks = env.barrier, env.max_over_ranks
 
     # ---- (1) resident loss step: fused kernel on the local rows + ONE exchange of the partials
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    ev_end = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    # The kernel is bracketed by CUDA events INSIDE the timed region, but only on every EVERY-th step: an event record between two
+    # launches costs a few microseconds of stream time and breaks their programmatic (PDL) chaining, which at 8 GPUs (0.2 ms steps)
+    # would be 5 % of the number being measured.
+    EVERY = 1 if K < 32 else 8
+    sampled = [k for k in range(K) if k % EVERY == 0]
+    ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for k in sampled}
+    ev_end = {k: torch.cuda.Event(enable_timing=True) for k in sampled}
     cursor = {"k": None}
 
     def timed(raw):  # the fused kernel, bracketed by events inside the timed region
         def fn(*a):
             k = cursor["k"]
-            if k is not None:
+            if k in ev:
                 ev[k][0].record()
             raw(*a)
-            if k is not None:
+            if k in ev:
                 ev[k][1].record()
         return fn
 
     def make_loss_fn(mode_bits, tgt, with_events=True):
         wrap = timed if with_events else (lambda f: f)
+        if world == 1:  # one GPU: the library call itself, results in place (no packed buffer, no unpack kernels)
+            m_out = torch.empty(N.PAIR_NMOM, dtype=torch.float64, device=dev)
+            g_out = torch.empty(n, 3, dtype=torch.float32, device=dev)
+            raw = wrap(lambda c: ops.pairloss_raw(c, tgt, mode_bits, c_mse, c_l1, moments=m_out, grad=g_out))
+
+            def single(c):
+                raw(c)
+                return m_out, g_out
+
+            return single
         const = None
-        if world > 1 and mode_bits & N.PAIR_MOMENTS_D and not mode_bits & N.PAIR_MOMENTS:
+        if mode_bits & N.PAIR_MOMENTS_D and not mode_bits & N.PAIR_MOMENTS:
             const = sharding.allreduce_packed(tgt.t_moments().clone())
         fn = sharding.make_sharded_pair_loss(n, wrap(sharding.cuda_local_fn(tgt, mode_bits, c_mse, c_l1)), dev, moment_const=const, transport=args.transport,
                                              local_split_fn=wrap(sharding.cuda_local_split_fn(tgt, mode_bits, c_mse, c_l1)))
@@ -622,7 +669,7 @@ def measure_workload(env: Env, name: str, primary: bool):
     def loss_step(k=None):
         cursor["k"] = k
         out = loss_fn(coords)
-        if k is not None:
+        if k in ev_end:
             ev_end[k].record()  # kernel end -> here = the exchange (barrier wait on the slowest rank + reduction) / nothing at 1 GPU
         return out
 
@@ -648,8 +695,8 @@ def measure_workload(env: Env, name: str, primary: bool):
         w1 = time.time()
         launches = N.launch_count() - launches0
         elapsed_ms = max_over_ranks(start.elapsed_time(stop))
-        kern_ms = sum(a.elapsed_time(b) for a, b in ev) / K
-        exch_ms = sum(ev[k][1].elapsed_time(ev_end[k]) for k in range(K)) / K
+        kern_ms = sum(a.elapsed_time(b) for a, b in ev.values()) / len(ev)
+        exch_ms = sum(ev[k][1].elapsed_time(ev_end[k]) for k in sampled) / len(sampled)
         # A host-side stall (noisy neighbour, GC) leaves the GPU queue empty and shows up as step time far above
         # the kernel time; like a throttled run it is re-measured ONCE and the fact is reported.
         stalled = max_over_ranks(1.0 if elapsed_ms / K > 1.25 * kern_ms + 0.1 else 0.0) > 0
@@ -667,9 +714,9 @@ def measure_workload(env: Env, name: str, primary: bool):
     streamed = (sum(n - i for i in (r0, r1 - 1)) / 2.0 * (r1 - r0) if r1 > r0 else 0.0) * 4.0 if upper else float(nloc) * n * 4.0
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     res = {"name": name, "n": n, "K": K, "W": W, "value": value, "ms_per_step": elapsed_ms / K, "kernel_ms": kern_ms, "exchange_ms": exch_ms, "launches": int(launches),
-           "attempts": attempts, "mse": mse, "nloc": nloc, "target_bytes": target_bytes, "transport": transport, "setup_s": round(t_setup, 1),
+           "attempts": attempts, "kernel_samples": len(sampled), "mse": mse, "nloc": nloc, "target_bytes": target_bytes, "transport": transport, "setup_s": round(t_setup, 1),
            "achieved": achieved, "peak": peak, "peak_src": peak_src, "loss_mode": loss_mode, "upper": upper, "alg_bytes": alg_bytes, "streamed_bytes": streamed,
-           "rows": [r0, r1], "balance": inp["balance"]}
+           "rows": [r0, r1], "balance": inp["balance"], "rebalance": inp["rebalance"], "cuts": inp["cuts"]}
 
     # ---- (1b) the other per-step mode of the training loops (MSE + Pearson moments in the same pass), briefly
     if primary and loss_mode == "mse":
@@ -973,12 +1020,13 @@ def run_native(args):
             "data": "synthetic" if w["kind"] == "synthetic" else "reference fixture (chr19)",
             "config": workload_config(name, res["loss_mode"]),
             "run": {"parallelism": f"rows{world}" if world > 1 else ("single" if not args.emulate_world else f"rank0-of-{args.emulate_world} (emulated, NOT a bench line)"),
-                    "rows_per_rank": nloc, "rows": res["rows"], "row_balance": res["balance"], "upper_triangle_only": res["upper"], "cpus_near_gpu": env.numa, "exchange": res["transport"], "exchange_ms": res["exchange_ms"],
+                    "rows_per_rank": nloc, "rows": res["rows"], "row_balance": res["balance"], "row_cuts": res["cuts"], "rebalance_rounds": res["rebalance"], "upper_triangle_only": res["upper"], "cpus_near_gpu": env.numa, "exchange": res["transport"], "exchange_ms": res["exchange_ms"],
                     "timed_attempts": res["attempts"], "l2": f"no flush: each step streams {res['target_bytes'] / 1e6:.0f} MB of target per rank (L2 is 126 MB)",
                     "setup_s": res["setup_s"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": ("pairloss_tma_kernel" if args.variant == 0 else "pairloss_ldg_kernel") + " + pairloss_combine_kernel", "kernel_ms": kern_ms,
-                         "note": "kernel_ms = CUDA events around the two launches of one loss evaluation; peak is a COPY bandwidth (half reads, half writes): a read-only stream can exceed it slightly; "
+                         "kernel_samples": res["kernel_samples"],
+                         "note": "kernel_ms = CUDA events around the two launches of one loss evaluation, on every 8th step of the timed region; peak is a COPY bandwidth (half reads, half writes): a read-only stream can exceed it slightly; "
                                  "traffic = dram bytes of the committed ncu capture of this shape (profiles/pairloss_traffic.json), not re-measured in this run",
                          "algorithmic_bytes": res["alg_bytes"], "streamed_bytes": res["streamed_bytes"],
                          "streamed_note": "upper-triangle mode: the target is symmetric, the kernel reads ~2 B per ordered pair (column >= row only) and evaluates every unordered pair once; "

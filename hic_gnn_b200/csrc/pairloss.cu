@@ -1354,6 +1354,17 @@ extern "C" int hicgat_pairloss_describe_schedule_mode(int64_t n, int64_t r0, int
     return k;
 }
 
+extern "C" double hicgat_pairloss_estimate_cost(int64_t n, int64_t r0, int64_t r1, uint32_t mode) {
+    if (n <= 0 || r0 < 0 || r1 < r0 || r1 > n) return -1.0;
+    if (r1 == r0) return 0.0;
+    const bool sym = g_variant == 0 && (mode & HICGAT_PAIR_SYMMETRIC) != 0;
+    const Layout L = make_layout(n, r0, r1, g_variant, sym);
+    if (sym) return simulate_upper(r0, L.nstrips, L.sch, L.stagger);
+    // full-matrix mode: every strip has every chunk
+    Schedule S = L.sch;
+    return simulate_upper(-(int64_t)n * 2, L.nstrips, S, L.stagger);  // a diagonal far to the left clips nothing
+}
+
 extern "C" size_t hicgat_pairloss_workspace_bytes(int64_t n, int64_t r0, int64_t r1) {
     if (n <= 0 || r0 < 0 || r1 < r0 || r1 > n) return 0;
     // for the CURRENT tuning (re-query after set_tuning); covers either variant

@@ -15,6 +15,7 @@ from torch import nn
 
 from . import _native as N
 from .graph import CSRGraph, as_graph
+from . import ops as _ops
 from .ops import _cuda, _stream
 
 
@@ -53,9 +54,9 @@ class SAGEConv(nn.Module):
         super().__init__()
         self.in_channels, self.out_channels = in_channels, out_channels
         self.normalize, self.root_weight, self.trunc_root = normalize, root_weight, trunc_root
-        self.lin_l = nn.Linear(in_channels, out_channels, bias=bias)
+        self.lin_l = _ops.Linear(in_channels, out_channels, bias=bias)
         if root_weight:
-            self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+            self.lin_r = _ops.Linear(in_channels, out_channels, bias=False)
 
     def forward(self, x, edge_index, edge_attr=None, size=None):
         graph = as_graph(edge_index, edge_attr, x.shape[0])
@@ -215,7 +216,7 @@ class GATConv(nn.Module):
         # message-passing path: "auto" = dense tiles when >= dense_threshold of all pairs are edges
         # (and the kernels support the shape), else the CSR warp-per-row kernels; "csr" / "dense" force one
         self.path, self.dense_threshold, self.dense_max_n = "auto", 0.35, 32768
-        self.lin_l = nn.Linear(in_channels, heads * out_channels, bias=False)
+        self.lin_l = _ops.Linear(in_channels, heads * out_channels, bias=False)
         self.lin_r = self.lin_l
         self.att_l = nn.Parameter(torch.empty(1, heads, out_channels))
         self.att_r = nn.Parameter(torch.empty(1, heads, out_channels))

@@ -13,10 +13,10 @@ from __future__ import annotations
 
 import torch.nn.functional as F
 from torch import nn
-from torch.nn import LayerNorm, Linear
+from torch.nn import LayerNorm
 
 from .layers import GATConv, SAGEConv
-from .ops import ln_relu_add, pairdist
+from .ops import Linear, ln_relu_add, pairdist  # Linear = nn.Linear whose GEMMs run on the tensor cores (3xTF32) on large maps
 
 
 class _CoordNet(nn.Module):

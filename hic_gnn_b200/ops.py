@@ -447,6 +447,87 @@ def ln_relu_add(x: torch.Tensor, norm: torch.nn.LayerNorm, residual: torch.Tenso
     return _LnReluAddFn.apply(x, residual, norm.weight, norm.bias, norm.eps)
 
 
+# ------------------------------------------------------------------------------ Linear layers on the tcgen05 tensor cores (3xTF32)
+TF32X3_MIN_ROWS = int(os.environ.get("HICGAT_TF32X3_MIN_ROWS", "4096"))  # below this the cuBLAS fp32 GEMM is launch-bound anyway
+_split_cache: dict = {}
+
+
+def split_tf32(x: torch.Tensor, pattern: int, transpose: bool = False, cache: bool = False) -> torch.Tensor:
+    """``hicgat_split_tf32``: ``[s0 | s1 | s2]`` along the reduction dimension, ``s_p`` = hi or lo TF32 part by bit p of ``pattern``
+    (0b100 for the left operand, 0b010 for the right one).  ``cache``: memoise for a constant tensor (the input features)."""
+    _cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise RuntimeError("split_tf32 expects a row-major float32 CUDA matrix")
+    key = (x.data_ptr(), x._version, tuple(x.shape), x.stride(0), pattern, transpose)
+    if cache and key in _split_cache:
+        return _split_cache[key]
+    rows, cols = x.shape
+    red = rows if transpose else cols
+    kpad = (red + 31) // 32 * 32
+    out = torch.empty(cols if transpose else rows, 3 * kpad, dtype=torch.float32, device=x.device)
+    N.check(N.lib().hicgat_split_tf32(x.data_ptr(), rows, cols, x.stride(0), out.data_ptr(), pattern, int(transpose), _stream()), "hicgat_split_tf32")
+    if cache:
+        if len(_split_cache) > 8:
+            _split_cache.clear()
+        _split_cache[key] = out
+    return out
+
+
+def gemm_tf32_tn(a_s: torch.Tensor, b_s: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
+    """``hicgat_gemm_tf32_tn``: ``a_s [m, k'] . b_s [n, k']^T (+ bias)`` on tcgen05 (operands from :func:`split_tf32`)."""
+    m, k = a_s.shape
+    n = b_s.shape[0]
+    assert b_s.shape[1] == k
+    d = torch.empty(m, n, dtype=torch.float32, device=a_s.device)
+    lib = N.lib()
+    wsb = lib.hicgat_gemm_tf32_workspace_bytes(m, n, k)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=a_s.device)
+    N.check(lib.hicgat_gemm_tf32_tn(a_s.data_ptr(), a_s.stride(0), b_s.data_ptr(), b_s.stride(0), m, n, k, _ptr(bias), d.data_ptr(), d.stride(0),
+                                    ws.data_ptr(), ws.numel(), _stream()), "hicgat_gemm_tf32_tn")
+    return d
+
+
+class _Linear3xTF32(torch.autograd.Function):
+    """``F.linear`` with all three GEMMs (y = x W^T + b, dx = dy W, dW = dy^T x) on the tensor cores at fp32 accuracy."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.contiguous()
+        w = weight.detach().contiguous()
+        y = gemm_tf32_tn(split_tf32(x.detach(), 0b100, cache=not x.requires_grad), split_tf32(w, 0b010), None if bias is None else bias.detach().contiguous())
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:  # dx[m, k] = dy[m, n] . (W^T)[k, n]^T : reduction over the output features
+            gx = gemm_tf32_tn(split_tf32(gy, 0b100), split_tf32(w, 0b010, transpose=True))
+        if ctx.needs_input_grad[1]:  # dW[n, k] = (dy^T)[n, m] . (x^T)[k, m]^T : reduction over the rows
+            gw = gemm_tf32_tn(split_tf32(gy, 0b100, transpose=True), split_tf32(x, 0b010, transpose=True, cache=not x.requires_grad))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(dim=0)
+        return gx, gw, gb
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
+    """``torch.nn.functional.linear`` of the MLP heads / the GATConv projection.  Maps of at least ``TF32X3_MIN_ROWS`` loci run the
+    three GEMMs on the tcgen05 tensor cores (3xTF32 split: fp32-level accuracy); smaller ones stay on the cuBLAS fp32 GEMM."""
+    if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[0] >= TF32X3_MIN_ROWS and weight.shape[0] >= 32 and TF32X3_MIN_ROWS > 0:
+        return _Linear3xTF32.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
+class Linear(torch.nn.Linear):
+    """``torch.nn.Linear`` (same parameters, init and ``state_dict`` keys) whose forward goes through :func:`linear`."""
+
+    def forward(self, x):
+        return linear(x, self.weight, self.bias)
+
+
 # ------------------------------------------------------------------------------ host-buffer entry
 class HostPairLoss:
     """Pairwise loss for a target that lives in (pinned) HOST memory: the row blocks are

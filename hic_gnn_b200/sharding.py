@@ -25,7 +25,7 @@ def row_block(n: int, rank: int, world: int, balance: str = "rows") -> tuple[int
 
     ``balance="rows"``: equal row counts (the kernels stream the full row block).
     ``balance="upper"``: equal UPPER-TRIANGLE area (symmetric targets: row i costs n - i pairs, so the first rank gets
-    few long rows and the last one many short ones); boundaries rounded to the kernel's 64-row tiles."""
+    few long rows and the last one many short ones); boundaries rounded to the kernel's 64-row tiles on big maps."""
     if balance == "rows":
         per = (n + world - 1) // world
         r0 = min(rank * per, n)
@@ -40,13 +40,46 @@ def row_block(n: int, rank: int, world: int, balance: str = "rows") -> tuple[int
             return n
         # rows [0, c) hold a fraction 1 - (1 - c/n)^2 of the triangle
         c = n * (1.0 - (1.0 - r / world) ** 0.5)
-        return max(0, min(n, int(round(c / 64.0)) * 64))
+        unit = 64 if n // world >= 2048 else 8  # big blocks: whole 64-row tiles; small ones: the rounding would unbalance them
+        return max(0, min(n, int(round(c / unit)) * unit))
 
     return cut(rank), cut(rank + 1)
 
 
 def all_blocks(n: int, world: int, balance: str = "rows") -> list[tuple[int, int]]:
     return [row_block(n, r, world, balance) for r in range(world)]
+
+
+def rebalance_cuts(n: int, cuts: list[int], times: list[float], unit: int = 64) -> list[int]:
+    """One step of MEASURED load balancing for the upper-triangle kernel: ``cuts`` (world + 1 row boundaries, cuts[0] = 0,
+    cuts[-1] = n) were run and rank r's kernel took ``times[r]``.  Equal-area blocks do not take equal time (a wide, short
+    block pays the per-item overhead more often than a tall triangle), so the cost per unit of triangle area is taken to be
+    constant INSIDE each measured block and the boundaries are moved to where the cumulative cost reaches k / world of the total.
+    Pure arithmetic (no GPU, no collectives): every rank calls it with the same gathered ``times`` and gets the same answer."""
+    world = len(cuts) - 1
+    if world < 2 or any(t <= 0 for t in times):
+        return list(cuts)
+
+    def frac(r):  # share of the upper triangle above row r
+        return 1.0 - (1.0 - r / n) ** 2
+
+    u = [frac(c) for c in cuts]
+    total = sum(times)
+    new = [0]
+    acc, k = 0.0, 0
+    for j in range(1, world):
+        want = total * j / world
+        while k < world - 1 and acc + times[k] < want:
+            acc += times[k]
+            k += 1
+        width = u[k + 1] - u[k]
+        uu = u[k] + (width * (want - acc) / times[k] if width > 0 else 0.0)
+        row = n * (1.0 - max(0.0, 1.0 - uu) ** 0.5)
+        uu_unit = unit if n // world >= 2048 else 8
+        row = int(round(row / uu_unit)) * uu_unit
+        new.append(max(new[-1], min(n, row)))
+    new.append(n)
+    return new
 
 
 def unpack(packed: torch.Tensor, n: int):

@@ -105,6 +105,10 @@ HICGAT_API int hicgat_memcpy2d_h2d_async(void* dst_device, size_t dst_pitch_byte
 #define HICGAT_PAIR_NMOM 8
 
 HICGAT_API size_t hicgat_pairloss_workspace_bytes(int64_t n, int64_t r0, int64_t r1);
+/* Host-side estimate of the kernel time of rows [r0,r1) under `mode` (makespan of the grid's chunk-major dispatch onto the CTA slots,
+ * in units of "one CTA streaming one row of its strip"; per-item overhead included).  Used to balance the row blocks of a sharded run
+ * by cost instead of by row count or area.  No GPU work. */
+HICGAT_API double hicgat_pairloss_estimate_cost(int64_t n, int64_t r0, int64_t r1, uint32_t mode);
 HICGAT_API size_t hicgat_pairloss_workspace_bytes_mode(int64_t n, int64_t r0, int64_t r1, uint32_t mode);
 HICGAT_API int hicgat_pairloss_fwd_bwd(const float* coords, const float* target, int64_t pitch, int64_t n,
                             int64_t r0, int64_t r1, uint32_t mode, float c_mse, float c_l1,
@@ -233,6 +237,25 @@ HICGAT_API int hicgat_pairdist_fwd(const float* coords, int64_t n, float* dist, 
                         hicgat_stream_t stream);
 HICGAT_API int hicgat_pairdist_bwd(const float* coords, int64_t n, const float* grad_dist, int64_t pitch,
                         float* grad_coords, hicgat_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * fp32-accurate Linear GEMMs on the tcgen05 tensor cores (3xTF32).  Replaces the ATen addmm of torch.nn.Linear in the MLP
+ * heads / the GATConv projection (models.py:23-55, 634-691, 1020-1047) and its two backward GEMMs on large maps.
+ *   hicgat_split_tf32: src [rows, cols] f32 (ld elements per row) -> dst = [s0 | s1 | s2] concatenated along the REDUCTION
+ *     dimension, s_p = tf32(a) ("hi") or tf32(a - tf32(a)) ("lo") by bit p of `pattern`:
+ *       transpose = 0: dst [rows, 3 kpad], reduction over the columns, kpad = cols rounded up to 32 (padding written as 0);
+ *       transpose = 1: dst [cols, 3 kpad], reduction over the rows,    kpad = rows rounded up to 32.
+ *     With A' = split(A, pattern 0b100) = [hi|hi|lo] and B' = split(B, pattern 0b010) = [hi|lo|hi],
+ *     A' . B'^T = A_hi B_hi + A_hi B_lo + A_lo B_hi  ~  A . B^T to ~2^-21.
+ *   hicgat_gemm_tf32_tn: d[m, n] (ldd) = a[m, k] . b[n, k]^T (+ bias[n]), a / b row-major f32 holding tf32-exact values,
+ *     k a multiple of 32.  tcgen05.mma kind::tf32, fp32 accumulator in TMEM, operands by TMA; split-K (deterministic reduce) when
+ *     the output tiles alone cannot fill the chip: pass a workspace of hicgat_gemm_tf32_workspace_bytes(m, n, k) bytes.
+ * ---------------------------------------------------------------------------------- */
+HICGAT_API int hicgat_split_tf32(const float* src, int64_t rows, int64_t cols, int64_t ld, float* dst, int pattern, int transpose,
+                      hicgat_stream_t stream);
+HICGAT_API size_t hicgat_gemm_tf32_workspace_bytes(int64_t m, int64_t n, int64_t k);
+HICGAT_API int hicgat_gemm_tf32_tn(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                        const float* bias, float* d, int64_t ldd, void* workspace, size_t workspace_bytes, hicgat_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Elementwise glue of the GAT net's MLP head between its (cuBLAS) Linear layers:

@@ -79,3 +79,22 @@ def test_row_blocks_cover_exactly():
             for (a0, a1), (b0, b1) in zip(blocks, blocks[1:]):
                 assert a1 == b0 and a0 <= a1
             assert sum(b - a for a, b in blocks) == n
+
+
+def test_upper_triangle_blocks_and_measured_rebalance():
+    """Area-balanced blocks of the upper-triangle kernel cover the rows exactly and carry equal triangle area; the measured rebalance
+    step moves boundaries towards the slow ranks and is a fixed point for equal times."""
+    for n in (9970, 49850):
+        for world in (2, 4, 8):
+            blocks = sharding.all_blocks(n, world, "upper")
+            assert blocks[0][0] == 0 and blocks[-1][1] == n and all(a1 == b0 for (_, a1), (b0, _) in zip(blocks, blocks[1:]))
+            area = [sum(n - i for i in range(a, b)) for a, b in blocks]
+            assert max(area) / min(area) < 1.08
+            cuts = [b[0] for b in blocks] + [n]
+            same = sharding.rebalance_cuts(n, cuts, [1.0] * world)
+            assert all(abs(a - b) <= 64 for a, b in zip(same, cuts))
+            times = [1.0] * world
+            times[0] = 1.2  # rank 0 slow: its block must shrink, everything stays ordered and covered
+            new = sharding.rebalance_cuts(n, cuts, times)
+            assert new[0] == 0 and new[-1] == n and all(a <= b for a, b in zip(new, new[1:])) and new[1] < cuts[1]
+    assert sharding.rebalance_cuts(100, [0, 100], [1.0]) == [0, 100]
