@@ -66,8 +66,8 @@ SIGNATURES = {
     "hicgat_gat_param_grads_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "hicgat_gat_param_grads": (C.c_int, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hicgat_split_tf32": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _i32, _p]),
-    "hicgat_gemm_tf32_workspace_bytes": (_sz, [_i64, _i64, _i64]),
-    "hicgat_gemm_tf32_tn": (C.c_int, [_p, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _sz, _p]),
+    "hicgat_gemm_tf32_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
+    "hicgat_gemm_tf32_tn": (C.c_int, [_p, _i64, _p, _i64, _i64, _i64, _i64, _i32, _p, _p, _i64, _p, _sz, _p]),
     "hicgat_ln_relu_add_fwd": (C.c_int, [_p, _p, _p, _p, _f32, _i64, _i32, _p, _p, _p, _p]),
     "hicgat_ln_relu_add_bwd_workspace_bytes": (_sz, [_i64, _i32]),
     "hicgat_ln_relu_add_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _sz, _p]),

@@ -12,7 +12,7 @@
 // Kernel (one CTA per 128 x BN output tile and K split; 6 warps):
 //   warp 0   TMA producer: cp.async.bulk.tensor.2d boxes of 128 rows x 32 tf32 (128 B, SWIZZLE_128B) of A' and BN x 32 of B'
 //            into a 4-stage shared-memory ring, completion on the stage's `full` mbarrier;
-//   warp 1   allocates BN TMEM columns; one elected lane issues 4 x tcgen05.mma.cta_group::1.kind::tf32 (128 x BN x 8) per
+//   warp 1   allocates 2 x BN TMEM columns (main product / cross terms, see the kernel); one elected lane issues 4 x tcgen05.mma.cta_group::1.kind::tf32 (128 x BN x 8) per
 //            stage from shared-memory matrix descriptors, tcgen05.commit frees the stage (`empty` mbarrier) and, after the last
 //            k-block, signals the accumulator (`acc` mbarrier);
 //   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns per instruction -> registers -> (+ bias) -> coalesced 128-byte row
@@ -104,6 +104,7 @@ struct GemmParams {
     float* d;            // [M, ldd] (ksplit == 1) or partials [ksplit][M][ldd]
     const float* bias;   // [N] or nullptr (added when ksplit == 1; otherwise by the reduce kernel)
     int m, n, kblocks, kb_per_split, ldd;
+    int kparts;          // 3: k-block kb is a main (hi.hi) block iff kb % 3 == 0, else a cross-term block -> accumulator 1; 1: plain GEMM
 };
 
 template <int BN, int STAGES>
@@ -132,8 +133,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_tn_kernel(const __g
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // one full warp allocates BN TMEM columns (power of two >= 32) and gives the permit back
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "n"(BN) : "memory");
+    // Two accumulators.  The tensor core adds every MMA result to the fp32 accumulator with TRUNCATION (measured: the error of one
+    // accumulator fed all 3K/8 steps of a 3xTF32 product is (3K/8) * 2^-24 / 2 = 5.8e-6 at K = 512, five times cuBLAS' fp32 SIMT
+    // error).  The two cross terms a_hi b_lo + a_lo b_hi are 2^-11 of the main product but cost 2/3 of those steps, so they get an
+    // accumulator of their own (its ulp is 2^-11 smaller: no visible error) and the epilogue adds the two in registers (round to nearest).
+    const bool use_main = nkb > 0, use_lo = P.kparts == 3 && nkb > 1;  // split ranges start at a multiple of 3 (plan_gemm)
+    if (warp == 1) {  // one full warp allocates 2 * BN TMEM columns (power of two >= 32) and gives the permit back
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_smem)), "n"(2 * BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -161,10 +167,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_tn_kernel(const __g
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a0 = smem_addr(tiles + (size_t)s * kStage), b0 = a0 + kABytes;
                 const uint64_t da = umma_desc_k_sw128(a0), db = umma_desc_k_sw128(b0);
+                const bool lo = P.kparts == 3 && ((kb0 + i) % 3) != 0;
+                const bool first = lo ? (i == 1) : (i == 0);  // kb0 is a multiple of 3: block 0 is main, block 1 the first cross-term block
 #pragma unroll
                 for (int k = 0; k < kBK / kUK; ++k) {
                     // advance along K inside the 128-byte swizzle atom: + k * 32 bytes on the start address (4 LSB dropped)
-                    umma_tf32(tmem_base, da + (uint64_t)(k * kUK * 4 >> 4), db + (uint64_t)(k * kUK * 4 >> 4), idesc, (i | k) ? 1u : 0u);
+                    umma_tf32(tmem_base + (lo ? (uint32_t)BN : 0u), da + (uint64_t)(k * kUK * 4 >> 4), db + (uint64_t)(k * kUK * 4 >> 4), idesc,
+                              (first && k == 0) ? 0u : 1u);
                 }
                 umma_commit(&empty_bar[s]);   // arrives when the MMAs above have finished reading this stage
             }
@@ -181,11 +190,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_tn_kernel(const __g
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             float v[32];
-            if (nkb > 0) {
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            if (use_main) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (use_lo) {
+                float u[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c), u);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += u[i];
             }
             if (row < P.m) {
                 const int col0 = tile_n * BN + c;
@@ -211,7 +223,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32_tn_kernel(const __g
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
     }
 }
 
@@ -221,9 +233,9 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)m * n) return;
     const int r = (int)(i / n), c = (int)(i - (int64_t)r * n);
-    float s = 0.f;
-    for (int z = 0; z < ksplit; ++z) s += part[((size_t)z * m + r) * ldd + c];
-    d[(size_t)r * ldo + c] = s + (bias ? bias[c] : 0.f);
+    double s = 0.0;
+    for (int z = 0; z < ksplit; ++z) s += (double)part[((size_t)z * m + r) * ldd + c];
+    d[(size_t)r * ldo + c] = (float)s + (bias ? bias[c] : 0.f);
 }
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -232,7 +244,9 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(r);
 }
 
-// dst = [s0 | s1 | s2] along the reduction dimension, s in {hi, lo} chosen by `pattern` bits (bit p set = lo for part p).
+// dst = the three parts s0, s1, s2 (s in {hi, lo} chosen by `pattern` bits: bit p set = lo for part p) INTERLEAVED per k-block of 32
+// along the reduction dimension: [s0(0:32) | s1(0:32) | s2(0:32) | s0(32:64) | ...], so that every run of 3 k-blocks of the GEMM holds one
+// main (hi.hi) block and its two cross-term blocks.
 //   transpose = 0: src [rows, cols] -> dst [rows, 3 * kpad]        (reduction over cols; kpad = cols rounded up to 32, padding zero)
 //   transpose = 1: src [rows, cols] -> dst [cols, 3 * kpad]        (reduction over rows; kpad = rows rounded up to 32)
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ src, int rows, int cols, int64_t lds, float* __restrict__ dst, int kpad,
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
             const float a = c < cols ? src[(size_t)r * lds + c] : 0.f;
             const float hi = to_tf32(a), lo = to_tf32(a - hi);
 #pragma unroll
-            for (int p = 0; p < 3; ++p) dst[(size_t)r * ldd + (size_t)p * kpad + c] = ((pattern >> p) & 1) ? lo : hi;
+            for (int p = 0; p < 3; ++p) dst[(size_t)r * ldd + (size_t)((c >> 5) * 3 + p) * 32 + (c & 31)] = ((pattern >> p) & 1) ? lo : hi;
         }
     } else {
 #pragma unroll
@@ -265,7 +279,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
             const float a = tile[tx][ty + 8 * k];
             const float hi = to_tf32(a), lo = to_tf32(a - hi);
 #pragma unroll
-            for (int p = 0; p < 3; ++p) dst[(size_t)c * ldd + (size_t)p * kpad + r] = ((pattern >> p) & 1) ? lo : hi;
+            for (int p = 0; p < 3; ++p) dst[(size_t)c * ldd + (size_t)((r >> 5) * 3 + p) * 32 + (r & 31)] = ((pattern >> p) & 1) ? lo : hi;
         }
     }
 }
@@ -299,7 +313,7 @@ struct GemmPlan {
 };
 // 128 x 256 tiles when there are enough of them to fill the chip twice over, else 128 x 128; split K when the tiles alone
 // leave SMs idle (the weight-gradient GEMMs: M, N <= 512 with K = 3 x loci)
-GemmPlan plan_gemm(int64_t m, int64_t n, int64_t k) {
+GemmPlan plan_gemm(int64_t m, int64_t n, int64_t k, int kparts) {
     GemmPlan g;
     g.kblocks = (k + kBK - 1) / kBK;
     const int64_t tm = (m + kBM - 1) / kBM, t128 = tm * ((n + 127) / 128);
@@ -308,6 +322,12 @@ GemmPlan plan_gemm(int64_t m, int64_t n, int64_t k) {
     int64_t ks = 1;
     if (tiles < 148) ks = std::min<int64_t>(std::max<int64_t>(148 / tiles, 1), std::max<int64_t>(g.kblocks / 16, 1));
     g.kb_per_split = (g.kblocks + ks - 1) / ks;
+    if (kparts == 3) {
+        // The tensor core truncates on every accumulation step: at most 16 main k-blocks (64 MMAs, ~2e-6) per accumulator; longer
+        // reductions (the weight-gradient GEMMs: K = 3 x loci) become more split-K partials, summed in f64 by the reduce kernel.
+        g.kb_per_split = (g.kb_per_split + 2) / 3 * 3;
+        if (g.kb_per_split > 48) g.kb_per_split = 48;
+    }
     g.ksplit = (g.kblocks + g.kb_per_split - 1) / g.kb_per_split;
     g.ldp = (n + 3) / 4 * 4;
     return g;
@@ -348,19 +368,20 @@ extern "C" int hicgat_split_tf32(const float* src, int64_t rows, int64_t cols, i
     return HICGAT_OK;
 }
 
-extern "C" size_t hicgat_gemm_tf32_workspace_bytes(int64_t m, int64_t n, int64_t k) {
+extern "C" size_t hicgat_gemm_tf32_workspace_bytes(int64_t m, int64_t n, int64_t k, int kparts) {
     if (m <= 0 || n <= 0 || k <= 0) return 0;
-    const GemmPlan g = plan_gemm(m, n, k);
+    const GemmPlan g = plan_gemm(m, n, k, kparts);
     return g.ksplit > 1 ? (size_t)g.ksplit * m * g.ldp * sizeof(float) : 0;
 }
 
-extern "C" int hicgat_gemm_tf32_tn(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int64_t n, int64_t k, const float* bias, float* d,
-                                   int64_t ldd, void* workspace, size_t workspace_bytes, hicgat_stream_t stream_) {
+extern "C" int hicgat_gemm_tf32_tn(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int64_t n, int64_t k, int kparts, const float* bias,
+                                   float* d, int64_t ldd, void* workspace, size_t workspace_bytes, hicgat_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     HICGAT_REQUIRE(a && b && d && m > 0 && n > 0 && k > 0 && m < (1ll << 30) && n < (1ll << 30) && k < (1ll << 30), "hicgat_gemm_tf32_tn: bad shape");
     HICGAT_REQUIRE(lda >= k && ldb >= k && ldd >= n && (lda % 4) == 0 && (ldb % 4) == 0 && aligned16(a) && aligned16(b) && aligned16(d),
                    "hicgat_gemm_tf32_tn: operands must be 16-byte aligned with leading dimensions that are multiples of 4");
-    const GemmPlan g = plan_gemm(m, n, k);
+    HICGAT_REQUIRE((kparts == 1 || kparts == 3) && (k % (kBK * kparts)) == 0, "hicgat_gemm_tf32_tn: k must be a multiple of 32 * kparts, kparts 1 or 3");
+    const GemmPlan g = plan_gemm(m, n, k, kparts);
     const int bn = g.wide ? 256 : 128;
     CUtensorMap ma, mb;
     if (!make_operand_map(&ma, a, m, k, lda, kBM) || !make_operand_map(&mb, b, n, k, ldb, bn)) {
@@ -369,6 +390,7 @@ extern "C" int hicgat_gemm_tf32_tn(const float* a, int64_t lda, const float* b, 
     }
     GemmParams P;
     P.bias = bias; P.m = (int)m; P.n = (int)n; P.kblocks = (int)g.kblocks; P.kb_per_split = (int)g.kb_per_split;
+    P.kparts = kparts;
     if (g.ksplit > 1) {
         HICGAT_REQUIRE(workspace && workspace_bytes >= (size_t)g.ksplit * m * g.ldp * sizeof(float) && aligned16(workspace), "hicgat_gemm_tf32_tn: workspace too small");
         P.d = static_cast<float*>(workspace);

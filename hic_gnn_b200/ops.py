@@ -459,17 +459,23 @@ def split_tf32(x: torch.Tensor, pattern: int, transpose: bool = False, cache: bo
     if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
         raise RuntimeError("split_tf32 expects a row-major float32 CUDA matrix")
     key = (x.data_ptr(), x._version, tuple(x.shape), x.stride(0), pattern, transpose)
-    if cache and key in _split_cache:
-        return _split_cache[key]
+    hit = _split_cache.get(key)
+    if hit is not None and hit[0] is x:  # the entry holds a reference to its source, so the address cannot have been recycled
+        return hit[1]
     rows, cols = x.shape
     red = rows if transpose else cols
     kpad = (red + 31) // 32 * 32
     out = torch.empty(cols if transpose else rows, 3 * kpad, dtype=torch.float32, device=x.device)
     N.check(N.lib().hicgat_split_tf32(x.data_ptr(), rows, cols, x.stride(0), out.data_ptr(), pattern, int(transpose), _stream()), "hicgat_split_tf32")
-    if cache:
-        if len(_split_cache) > 8:
-            _split_cache.clear()
-        _split_cache[key] = out
+    # memo: constant tensors (`cache`: the input features, split once per run) and, briefly, the latest activations (two Linear
+    # layers that read the same tensor -- densea / align_densea -- share one split)
+    if not cache:
+        for k in [k for k, v in _split_cache.items() if not v[2]]:
+            if len(_split_cache) > 6:
+                del _split_cache[k]
+    elif len(_split_cache) > 12:
+        _split_cache.clear()
+    _split_cache[key] = (x, out, cache)
     return out
 
 
@@ -480,9 +486,9 @@ def gemm_tf32_tn(a_s: torch.Tensor, b_s: torch.Tensor, bias: torch.Tensor | None
     assert b_s.shape[1] == k
     d = torch.empty(m, n, dtype=torch.float32, device=a_s.device)
     lib = N.lib()
-    wsb = lib.hicgat_gemm_tf32_workspace_bytes(m, n, k)
+    wsb = lib.hicgat_gemm_tf32_workspace_bytes(m, n, k, 3)
     ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=a_s.device)
-    N.check(lib.hicgat_gemm_tf32_tn(a_s.data_ptr(), a_s.stride(0), b_s.data_ptr(), b_s.stride(0), m, n, k, _ptr(bias), d.data_ptr(), d.stride(0),
+    N.check(lib.hicgat_gemm_tf32_tn(a_s.data_ptr(), a_s.stride(0), b_s.data_ptr(), b_s.stride(0), m, n, k, 3, _ptr(bias), d.data_ptr(), d.stride(0),
                                     ws.data_ptr(), ws.numel(), _stream()), "hicgat_gemm_tf32_tn")
     return d
 
@@ -516,7 +522,9 @@ class _Linear3xTF32(torch.autograd.Function):
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
     """``torch.nn.functional.linear`` of the MLP heads / the GATConv projection.  Maps of at least ``TF32X3_MIN_ROWS`` loci run the
     three GEMMs on the tcgen05 tensor cores (3xTF32 split: fp32-level accuracy); smaller ones stay on the cuBLAS fp32 GEMM."""
-    if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[0] >= TF32X3_MIN_ROWS and weight.shape[0] >= 32 and TF32X3_MIN_ROWS > 0:
+    # measured at 49 850 rows (profiles/r2_gemm.json): 512x512 and 512x256 layers run 1.5-2x faster than the cuBLAS fp32 GEMM incl. the
+    # split kernels, 256x128 and smaller are a wash or slower (the splits dominate): those stay on cuBLAS
+    if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[0] >= TF32X3_MIN_ROWS and weight.numel() >= 100000 and TF32X3_MIN_ROWS > 0:
         return _Linear3xTF32.apply(x, weight, bias)
     return torch.nn.functional.linear(x, weight, bias)
 

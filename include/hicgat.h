@@ -241,20 +241,25 @@ HICGAT_API int hicgat_pairdist_bwd(const float* coords, int64_t n, const float* 
 /* ------------------------------------------------------------------------------------
  * fp32-accurate Linear GEMMs on the tcgen05 tensor cores (3xTF32).  Replaces the ATen addmm of torch.nn.Linear in the MLP
  * heads / the GATConv projection (models.py:23-55, 634-691, 1020-1047) and its two backward GEMMs on large maps.
- *   hicgat_split_tf32: src [rows, cols] f32 (ld elements per row) -> dst = [s0 | s1 | s2] concatenated along the REDUCTION
- *     dimension, s_p = tf32(a) ("hi") or tf32(a - tf32(a)) ("lo") by bit p of `pattern`:
+ *   hicgat_split_tf32: src [rows, cols] f32 (ld elements per row) -> dst = the three parts s0, s1, s2 interleaved per 32 elements
+ *     along the REDUCTION dimension ([s0(0:32) | s1(0:32) | s2(0:32) | s0(32:64) | ...]), s_p = tf32(a) ("hi") or tf32(a - tf32(a))
+ *     ("lo") by bit p of `pattern`:
  *       transpose = 0: dst [rows, 3 kpad], reduction over the columns, kpad = cols rounded up to 32 (padding written as 0);
  *       transpose = 1: dst [cols, 3 kpad], reduction over the rows,    kpad = rows rounded up to 32.
  *     With A' = split(A, pattern 0b100) = [hi|hi|lo] and B' = split(B, pattern 0b010) = [hi|lo|hi],
  *     A' . B'^T = A_hi B_hi + A_hi B_lo + A_lo B_hi  ~  A . B^T to ~2^-21.
  *   hicgat_gemm_tf32_tn: d[m, n] (ldd) = a[m, k] . b[n, k]^T (+ bias[n]), a / b row-major f32 holding tf32-exact values,
- *     k a multiple of 32.  tcgen05.mma kind::tf32, fp32 accumulator in TMEM, operands by TMA; split-K (deterministic reduce) when
- *     the output tiles alone cannot fill the chip: pass a workspace of hicgat_gemm_tf32_workspace_bytes(m, n, k) bytes.
+ *     k a multiple of 32 * kparts.  kparts = 3: the operands are hicgat_split_tf32 outputs; the main (hi.hi) k-blocks and the
+ *     cross-term k-blocks accumulate in SEPARATE TMEM accumulators that the epilogue adds, and no accumulator takes more than 16 main
+ *     k-blocks (the tensor core truncates on every accumulation step: one accumulator fed all 3K/8 steps is off by 5.8e-6 at K = 512
+ *     and by 4e-5 at K = 50k); longer reductions run split-K with an f64 reduce;
+ *     kparts = 1: plain TF32 GEMM.  tcgen05.mma kind::tf32, operands by TMA; split-K (deterministic reduce) when the output tiles
+ *     alone cannot fill the chip: pass a workspace of hicgat_gemm_tf32_workspace_bytes(m, n, k) bytes.
  * ---------------------------------------------------------------------------------- */
 HICGAT_API int hicgat_split_tf32(const float* src, int64_t rows, int64_t cols, int64_t ld, float* dst, int pattern, int transpose,
                       hicgat_stream_t stream);
-HICGAT_API size_t hicgat_gemm_tf32_workspace_bytes(int64_t m, int64_t n, int64_t k);
-HICGAT_API int hicgat_gemm_tf32_tn(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+HICGAT_API size_t hicgat_gemm_tf32_workspace_bytes(int64_t m, int64_t n, int64_t k, int kparts);
+HICGAT_API int hicgat_gemm_tf32_tn(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t m, int64_t n, int64_t k, int kparts,
                         const float* bias, float* d, int64_t ldd, void* workspace, size_t workspace_bytes, hicgat_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
