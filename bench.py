@@ -1009,7 +1009,7 @@ def run_native(args):
         peak, achieved = res["peak"], res["achieved"]
         traffic = None  # DRAM bytes per launch from the committed ncu capture of this exact shape, if there is one
         try:
-            t = json.load(open(os.path.join(ROOT, "profiles", "pairloss_traffic.json"))).get(f"{nloc}x{n}")
+            t = json.load(open(os.path.join(ROOT, "profiles", "pairloss_traffic.json"))).get(f"{nloc}x{n}" + ("_upper" if res["upper"] else ""))
             if t and args.variant == 0:
                 traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"] + t.get("combine_dram_bytes_read", 0))
         except Exception:
