@@ -238,6 +238,14 @@ struct Params {
     int upper;
     int64_t rpitch;
     float* rpart;
+    // persistent variant: items = active (chunk, strip) pairs in chunk-major order; item_base[c] = first item of chunk c
+    unsigned* work_counter;   // zero before the launch, reset by the combine kernel
+    int nitems;
+    int item_base[kMaxChunks + 1];
+    // static warp partition (variant 4): the strip-major sequence of (strip, row) work is cut into equal runs of seg_len rows,
+    // one per warp; the partial of (strip s, warp w) lives in slot (w - first_warp(s)) * nstrips + s
+    int64_t seg_len, seg_total;
+    int seg_sa, seg_sb, seg_f;   // closed form of the rows per strip, see strip_offset()
 };
 
 struct ColumnRegs {
@@ -384,7 +392,9 @@ __device__ __forceinline__ int chunk_rows(const Params& P, int strip, int chunk,
     return count;
 }
 // number of leading chunks of `strip` that hold rows at all (all of them unless upper-triangle mode clips the strip)
+__device__ __forceinline__ int strip_segments(const Params& P, int s);
 __device__ __forceinline__ int active_chunks(const Params& P, int strip) {
+    if (P.seg_len > 0) return strip_segments(P, strip);  // static warp partition: one partial per warp that touched the strip
     const int par = strip_parity(P, strip);
     int count = P.sch.count[par];
     if (P.upper) {
@@ -498,6 +508,7 @@ __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const
         const bool live = pass == npass - 1;
         if (live) {
             pdl_wait();  // no-op when launched without the programmatic-serialization attribute
+            if (P.work_counter && blockIdx.x == 0 && tid == 0) *P.work_counter = 0u;  // the persistent kernel's item counter, for the next launch
 #ifdef HICGAT_TRACE
             if (ctr) ctr[1] = gtimer();
 #endif
@@ -543,7 +554,7 @@ __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const
             for (int k = 0; k < kNM; ++k) m[k] = 0.0;
             // every strip has the chunks 0 .. cmin-1; the chunk rows above have holes (strips of the other parity).
             // Upper-triangle mode: a strip has only its leading chunks (rows up to its last column).
-            const int cmin = P.upper ? 0 : min(P.sch.count[0], P.stagger ? P.sch.count[1] : P.sch.count[0]);
+            const int cmin = (P.upper || P.seg_len > 0) ? 0 : min(P.sch.count[0], P.stagger ? P.sch.count[1] : P.sch.count[0]);
             const int nfull = P.nstrips * cmin;
 #pragma unroll 4
             for (int sl = tid; sl < nfull; sl += kCombineThreads) {
@@ -943,6 +954,357 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_tma_kernel(cons
     HICGAT_TR(5);
 }
 
+// ------------------------------------------------------------------ variant 3: persistent CTAs, dynamic item queue
+// Same tiles, arithmetic and partial layout as pairloss_tma_kernel, but 2 x 148 CTAs stay resident and pull (chunk, strip) items
+// from an atomic counter.  What it buys on small row blocks (a 1/8 shard of the 50k-locus map, the 10k-locus map), where the
+// one-CTA-per-item kernel loses 25-40 % to the per-item prologue (~5 us: barrier init, tensor-map fetch, first-tile latency, column
+// loads, exit) and to wave quantisation:
+//   * a warp that has finished its rows of the current item immediately issues the first TMA boxes of the NEXT item into its ring
+//     (the ring and its mbarrier phases simply run on across items), so the next item's data is in flight during the CTA-level combine;
+//   * items can be short (128 .. 2048 rows), and the queue balances them dynamically: the slots run dry within one short item.
+// Partials are still stored per item (chunk * nstrips + strip) and summed by the combine kernel in a fixed order, so the result does
+// not depend on which CTA processed which item: bit-reproducible.
+struct PersistSmem {
+    float g[kWarps / 2][kCols * 3 + 4];   // two-phase CTA combine: the upper half of the warps parks, the lower half adds
+    double m[kWarps][kNM];
+    int item[2];
+};
+constexpr int kPersistSmem = kTmaSmem;     // the ring only: the combine area is static shared memory (it must not alias a ring in use)
+
+__device__ __forceinline__ void decode_item(const Params& P, int item, int& strip, int& chunk, int& row_begin, int& nrows) {
+    int lo = 0, hi = P.sch.count[0];  // item_base[lo] <= item < item_base[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (P.item_base[mid] <= item) lo = mid; else hi = mid;
+    }
+    chunk = lo;
+    const int first_strip = P.nstrips - (P.item_base[lo + 1] - P.item_base[lo]);
+    strip = first_strip + (item - P.item_base[lo]);
+    chunk_rows(P, strip, chunk, row_begin, nrows);
+}
+
+template <uint32_t MODE, bool ROWS>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_tma_persist_kernel(const __grid_constant__ CUtensorMap tmap, const Params P) {
+    pdl_launch_dependents();
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    __shared__ __align__(8) uint64_t full_bar[kWarps][kStages];
+    __shared__ PersistSmem S;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = P.n;
+    unsigned char* wring = ring + (size_t)warp * (kStages * kSlotBytes);
+    const uint32_t wring_s = smem_u32(wring);
+    const int wrow = warp * kU;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    }
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        S.item[0] = (int)atomicAdd(P.work_counter, 1u);
+        S.item[1] = (int)atomicAdd(P.work_counter, 1u);
+    }
+    __syncthreads();
+
+    const int xi_row = lane / 3, xi_comp = lane - xi_row * 3;
+    const uint32_t xi_off = kSubTileBytes + (xi_comp < 2 ? xi_row * 16 + xi_comp * 8 : kU * 16 + xi_row * 8);
+    unsigned gt = 0;  // tiles this warp has issued so far: tile g lives in slot g % kStages and is the (g / kStages)-th use of it
+
+    // x_i of tile t of an item: lane k < 24 owns component k % 3 of row k / 3 (stored duplicated (v, v) next to the tile)
+    auto xi_fetch = [&](int row_begin, int t) -> float {
+        const int gr = min(row_begin + t * kTileRows + wrow + xi_row, n - 1);
+        return lane < 24 ? __ldg(P.coords + (size_t)gr * 3 + xi_comp) : 0.f;
+    };
+    // issue tile t of an item (row_begin, strip) as this warp's ring entry number g; v = xi_fetch(row_begin, t), fetched earlier
+    auto issue = [&](int strip, int row_begin, int t, unsigned g, float v) {
+        const int s = (int)(g % kStages);
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&full_bar[warp][s], (uint32_t)kSubTileBytes);
+            tma_load_2d(wring + (size_t)s * kSlotBytes, &tmap, strip * kCols, (row_begin - P.r0) + t * kTileRows + wrow, &full_bar[warp][s]);
+        }
+        if (lane < 24) sts_f2(wring_s + s * kSlotBytes + xi_off, v, v);
+    };
+
+    int cur = S.item[0], nxt = S.item[1];
+    int strip = 0, chunk = 0, row_begin = 0, nrows = 0;
+    if (cur < P.nitems) {
+        decode_item(P, cur, strip, chunk, row_begin, nrows);
+        const int nt = (nrows + kTileRows - 1) / kTileRows;
+        for (int t = 0; t < kStages && t < nt; ++t) issue(strip, row_begin, t, gt + t, xi_fetch(row_begin, t));
+    }
+    __syncwarp();
+    for (int it = 0; cur < P.nitems; ++it) {
+        const int ntiles = (nrows + kTileRows - 1) / kTileRows;
+        const int col0 = strip * kCols + lane * 4;
+        const bool edge = (strip + 1) * kCols > n;
+        const int strip_lo = strip * kCols, strip_hi = strip_lo + kCols - 1;
+        ColumnRegs c;
+        load_columns(c, P.coords, col0, n);
+        Acc a;
+        acc_zero(a);
+        for (int t = 0; t < ntiles; ++t) {
+            const unsigned g = gt + t;
+            const int s = (int)(g % kStages);
+            const bool refill = t + kStages < ntiles;
+            const float xi_next = refill ? xi_fetch(row_begin, t + kStages) : 0.f;   // in flight during the compute below
+            mbar_wait(&full_bar[warp][s], (g / kStages) & 1u);
+            const uint32_t slot = wring_s + s * kSlotBytes;
+            const XiAddr xi{slot + kSubTileBytes, slot + kSubTileBytes + kU * 16};
+            const int rows_here = max(0, min(kU, nrows - (t * kTileRows + wrow)));
+            float4 tv[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) tv[u] = lds_f4(slot + lane * 16 + u * (kCols * 4));
+            const int rg = row_begin + t * kTileRows + wrow;
+            process_group<MODE, ROWS>(a, c, tv, xi, rows_here, rg, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1,
+                                      ROWS ? P.rpart + (size_t)strip * P.rpitch + (size_t)(rg - P.r0) * 3 : nullptr, lane);
+            __syncwarp();  // every lane is done with slot s
+            if (refill) issue(strip, row_begin, t + kStages, g + kStages, xi_next);
+        }
+        gt += (unsigned)ntiles;
+        // this warp's ring is empty: start the NEXT item's first tiles before the CTA-level combine
+        int nstrip = 0, nchunk = 0, nrow_begin = 0, nnrows = 0;
+        if (nxt < P.nitems) {
+            decode_item(P, nxt, nstrip, nchunk, nrow_begin, nnrows);
+            const int nt = (nnrows + kTileRows - 1) / kTileRows;
+            for (int t = 0; t < kStages && t < nt; ++t) issue(nstrip, nrow_begin, t, gt + t, xi_fetch(nrow_begin, t));
+        }
+        // ---- CTA combine in two phases (half the shared memory): warps 4..7 park, warps 0..3 add their own on top
+        constexpr bool kMom = (MODE & (kMomFull | kMomLight)) != 0;
+        {
+            double m[kNM];
+#pragma unroll
+            for (int k = 0; k < kNM; ++k) m[k] = 0.0;
+            const double seu = (double)f2_hsum(a.seu);
+            m[0] = (double)f2_hsum(a.see) + (ROWS ? 2.0 * seu : seu);
+            if constexpr (kMom) {
+                m[2] = (double)f2_hsum(a.sd); m[3] = (double)f2_hsum(a.sdd); m[6] = (double)f2_hsum(a.sdt); m[7] = seu;
+                if constexpr ((MODE & kMomFull) != 0) {
+                    m[1] = (double)a.sabs0 + (double)a.sabs1; m[4] = (double)f2_hsum(a.st); m[5] = (double)f2_hsum(a.stt);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kNM; ++k)
+                if (k == 0 || kMom) m[k] = warp_sum(m[k]);
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < kNM; ++k) S.m[warp][k] = m[k];
+            }
+        }
+        float gv[2][6];
+        if constexpr ((MODE & 3u) != 0) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                f2_unpack(a.gx[p], gv[p][0], gv[p][3]);
+                f2_unpack(a.gy[p], gv[p][1], gv[p][4]);
+                f2_unpack(a.gz[p], gv[p][2], gv[p][5]);
+            }
+            if (warp >= kWarps / 2) {
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    float* dst = &S.g[warp - kWarps / 2][(lane * 4 + 2 * p) * 3];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) dst[q] = gv[p][q];
+                }
+            }
+        }
+        __syncthreads();
+        if constexpr ((MODE & 3u) != 0) {
+            if (warp < kWarps / 2) {
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    float* dst = &S.g[warp][(lane * 4 + 2 * p) * 3];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) dst[q] += gv[p][q];   // fixed order: (w + 4) + w
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const int cta = chunk * P.nstrips + strip;
+            if constexpr ((MODE & 3u) != 0) {
+                float* gp = P.gpart + (size_t)cta * (kCols * 3);
+                for (int i = threadIdx.x; i < kCols * 3; i += kThreads) {
+                    float sum = 0.f;
+#pragma unroll
+                    for (int w = 0; w < kWarps / 2; ++w) sum += S.g[w][i];
+                    __stcg(gp + i, sum);
+                }
+            }
+            if (threadIdx.x < kNM) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) sum += S.m[w][threadIdx.x];
+                __stcg(P.mpart + (size_t)cta * kNM + threadIdx.x, sum);
+            }
+            if (threadIdx.x == 0) S.item[it & 1] = (int)atomicAdd(P.work_counter, 1u);  // the item after next
+        }
+        __syncthreads();
+        cur = nxt;
+        nxt = S.item[it & 1];
+        strip = nstrip; chunk = nchunk; row_begin = nrow_begin; nrows = nnrows;
+    }
+}
+
+// ------------------------------------------------------------------ variant 4: static warp partition
+// For SMALL row blocks (a 1/8 shard of the 50k-locus map, the 10k-locus map) the item kernels lose 25-40 % to per-item overhead and to
+// the last, partly filled wave.  Here nothing is dispatched at all: the work of the block, written as the strip-major sequence of
+// (strip, row) units -- strip s contributes rows_s = clamp(128 (s + 1) - r0, 0, nrows) units in upper-triangle mode, nrows otherwise --
+// is cut into 2 368 equal runs, one per resident warp (2 CTAs x 8 warps x 148 SMs).  A warp streams its run through its own TMA ring in
+// 8-row tiles, publishes one partial per strip it touches (1-3) straight from its registers, and exits: no CTA-level synchronisation,
+// no queue, no tail beyond one tile.  rows_s is piecewise linear in s, so strip offsets and their inverse are closed forms (no tables).
+// Partials are indexed by (strip, segment) and summed by the combine kernel in segment (= row) order: bit-reproducible.
+__device__ __forceinline__ int64_t strip_rows_of(const Params& P, int s) {
+    if (!P.upper) return P.r1 - P.r0;
+    const int64_t v = (int64_t)(s + 1) * kCols - P.r0;
+    const int64_t nrows = P.r1 - P.r0;
+    return v < 0 ? 0 : (v > nrows ? nrows : v);
+}
+// number of (strip, row) units before strip s
+__device__ __forceinline__ int64_t strip_offset(const Params& P, int s) {
+    const int64_t nrows = P.r1 - P.r0;
+    if (!P.upper) return (int64_t)s * nrows;
+    if (s <= P.seg_sa) return 0;
+    const int64_t m = (s < P.seg_sb ? s : P.seg_sb) - P.seg_sa;       // strips in the growing part
+    int64_t off = m * P.seg_f + 64 * m * (m - 1);
+    if (s > P.seg_sb) off += (int64_t)(s - P.seg_sb) * nrows;
+    return off;
+}
+__device__ __forceinline__ int strip_of_unit(const Params& P, int64_t p) {
+    const int64_t nrows = P.r1 - P.r0;
+    if (!P.upper) return (int)(p / nrows);
+    const int64_t off_b = strip_offset(P, P.seg_sb);
+    if (p >= off_b) return P.seg_sb + (int)((p - off_b) / nrows);
+    // largest m with m f + 64 m (m - 1) <= p
+    const double b = (double)P.seg_f - 64.0;
+    int64_t m = (int64_t)((-b + sqrt(b * b + 256.0 * (double)p)) / 128.0);
+    if (m < 0) m = 0;
+    while (m > 0 && m * P.seg_f + 64 * m * (m - 1) > p) --m;
+    while ((m + 1) * P.seg_f + 64 * (m + 1) * m <= p) ++m;
+    return P.seg_sa + (int)m;
+}
+__device__ __forceinline__ int strip_segments(const Params& P, int s) {  // warps that touch strip s
+    const int64_t rows = strip_rows_of(P, s);
+    if (rows <= 0) return 0;
+    const int64_t off = strip_offset(P, s);
+    return (int)((off + rows - 1) / P.seg_len - off / P.seg_len) + 1;
+}
+
+template <uint32_t MODE, bool ROWS>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) pairloss_tma_warp_kernel(const __grid_constant__ CUtensorMap tmap, const Params P) {
+    pdl_launch_dependents();
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    __shared__ __align__(8) uint64_t full_bar[kWarps][kStages];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = P.n;
+    unsigned char* wring = ring + (size_t)warp * (kStages * kSlotBytes);
+    const uint32_t wring_s = smem_u32(wring);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    }
+    pdl_wait();
+    __syncwarp();
+    const int64_t gw = (int64_t)blockIdx.x * kWarps + warp;
+    int64_t p = gw * P.seg_len;
+    const int64_t pend = p + P.seg_len < P.seg_total ? p + P.seg_len : P.seg_total;
+    const int xi_row = lane / 3, xi_comp = lane - xi_row * 3;
+    const uint32_t xi_off = kSubTileBytes + (xi_comp < 2 ? xi_row * 16 + xi_comp * 8 : kU * 16 + xi_row * 8);
+    unsigned gt = 0;
+    while (p < pend) {
+        const int strip = strip_of_unit(P, p);
+        const int64_t soff = strip_offset(P, strip);
+        const int row_lo = (int)(p - soff);                                  // local rows (offsets from r0) of this strip
+        int64_t take = strip_rows_of(P, strip) - row_lo;
+        if (take > pend - p) take = pend - p;
+        const int nrows = (int)take;
+        const int row_begin = P.r0 + row_lo;
+        const int ntiles = (nrows + kU - 1) / kU;
+        const int col0 = strip * kCols + lane * 4;
+        const bool edge = (strip + 1) * kCols > n;
+        const int strip_lo = strip * kCols, strip_hi = strip_lo + kCols - 1;
+        auto xi_fetch = [&](int t) -> float {
+            const int gr = min(row_begin + t * kU + xi_row, n - 1);
+            return lane < 24 ? __ldg(P.coords + (size_t)gr * 3 + xi_comp) : 0.f;
+        };
+        auto issue = [&](int t, unsigned g, float v) {
+            const int s = (int)(g % kStages);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full_bar[warp][s], (uint32_t)kSubTileBytes);
+                tma_load_2d(wring + (size_t)s * kSlotBytes, &tmap, strip * kCols, row_lo + t * kU, &full_bar[warp][s]);
+            }
+            if (lane < 24) sts_f2(wring_s + s * kSlotBytes + xi_off, v, v);
+        };
+        for (int t = 0; t < kStages && t < ntiles; ++t) issue(t, gt + t, xi_fetch(t));
+        ColumnRegs c;
+        load_columns(c, P.coords, col0, n);
+        Acc a;
+        acc_zero(a);
+        __syncwarp();
+        for (int t = 0; t < ntiles; ++t) {
+            const unsigned g = gt + t;
+            const int s = (int)(g % kStages);
+            const bool refill = t + kStages < ntiles;
+            const float xi_next = refill ? xi_fetch(t + kStages) : 0.f;
+            mbar_wait(&full_bar[warp][s], (g / kStages) & 1u);
+            const uint32_t slot = wring_s + s * kSlotBytes;
+            const XiAddr xi{slot + kSubTileBytes, slot + kSubTileBytes + kU * 16};
+            const int rows_here = min(kU, nrows - t * kU);
+            float4 tv[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) tv[u] = lds_f4(slot + lane * 16 + u * (kCols * 4));
+            const int rg = row_begin + t * kU;
+            process_group<MODE, ROWS>(a, c, tv, xi, rows_here, rg, col0, n, edge, strip_lo, strip_hi, P.c_mse, P.c_l1,
+                                      ROWS ? P.rpart + (size_t)strip * P.rpitch + (size_t)(rg - P.r0) * 3 : nullptr, lane);
+            __syncwarp();
+            if (refill) issue(t + kStages, g + kStages, xi_next);
+        }
+        gt += (unsigned)ntiles;
+        // ---- publish this warp's partial of the strip: slot (segment index, strip)
+        const int seg = (int)(gw - soff / P.seg_len);
+        const size_t slot_id = (size_t)seg * P.nstrips + strip;
+        if constexpr ((MODE & 3u) != 0) {
+            float* gp = P.gpart + slot_id * (kCols * 3) + lane * 12;
+            float x0, x1, y0, y1, z0, z1, x2, x3, y2, y3, z2, z3;
+            f2_unpack(a.gx[0], x0, x1); f2_unpack(a.gy[0], y0, y1); f2_unpack(a.gz[0], z0, z1);
+            f2_unpack(a.gx[1], x2, x3); f2_unpack(a.gy[1], y2, y3); f2_unpack(a.gz[1], z2, z3);
+            __stcg(reinterpret_cast<float4*>(gp), make_float4(x0, y0, z0, x1));
+            __stcg(reinterpret_cast<float4*>(gp) + 1, make_float4(y1, z1, x2, y2));
+            __stcg(reinterpret_cast<float4*>(gp) + 2, make_float4(z2, x3, y3, z3));
+        }
+        {
+            constexpr bool kMom = (MODE & (kMomFull | kMomLight)) != 0;
+            double m[kNM];
+#pragma unroll
+            for (int k = 0; k < kNM; ++k) m[k] = 0.0;
+            const double seu = (double)f2_hsum(a.seu);
+            m[0] = (double)f2_hsum(a.see) + (ROWS ? 2.0 * seu : seu);
+            if constexpr (kMom) {
+                m[2] = (double)f2_hsum(a.sd); m[3] = (double)f2_hsum(a.sdd); m[6] = (double)f2_hsum(a.sdt); m[7] = seu;
+                if constexpr ((MODE & kMomFull) != 0) {
+                    m[1] = (double)a.sabs0 + (double)a.sabs1; m[4] = (double)f2_hsum(a.st); m[5] = (double)f2_hsum(a.stt);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kNM; ++k)
+                if (k == 0 || kMom) m[k] = warp_sum(m[k]);
+            if (lane < kNM) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < kNM; ++k) v = lane == k ? m[k] : v;
+                __stcg(P.mpart + slot_id * kNM + lane, v);
+            }
+        }
+        p += take;
+    }
+}
+
 // ------------------------------------------------------------------ materialising variant
 __global__ void pairdist_fwd_kernel(const float* __restrict__ coords, int n, float* __restrict__ dist, int64_t pitch) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1020,8 +1382,13 @@ struct Layout {
     int nstrips, rb, nchunks, stagger;
     Schedule sch;
     size_t nslots;           // partial slots in gpart / mpart = nstrips * nchunks
-    size_t off_gpart, off_mpart, off_rpart, total;
+    size_t off_gpart, off_mpart, off_rpart, off_counter, total;
     int64_t rpitch;          // upper-triangle mode: floats per strip in rpart (0 otherwise)
+    int persistent;          // variant 3: item queue
+    int nitems;
+    int item_base[kMaxChunks + 1];
+    int64_t seg_len, seg_total;  // variant 4: static warp partition (seg_len = 0 otherwise)
+    int seg_sa, seg_sb, seg_f, seg_warps;
 };
 
 int g_tail_depth = -1;    // -1 = library default; >= 0: hicgat_pairloss_set_schedule
@@ -1111,10 +1478,62 @@ Layout make_layout_uncached(int64_t n, int64_t r0, int64_t r1, int variant, bool
     Layout L;
     L.nstrips = (int)((n + kCols - 1) / kCols);
     const int64_t nrows = r1 - r0;
+    L.persistent = variant == 3 ? 1 : 0;
+    L.seg_len = L.seg_total = 0;
+    L.seg_sa = L.seg_sb = L.seg_f = L.seg_warps = 0;
+    if (variant == 4 && nrows > 0) {
+        // static warp partition: closed form of rows per strip (see strip_offset) and the run length per warp
+        L.seg_sa = sym ? (int)(r0 / kCols) : 0;
+        L.seg_f = sym ? (int)(kCols - (r0 % kCols)) : 0;
+        L.seg_sb = sym ? L.seg_sa + (int)((std::max<int64_t>(nrows - L.seg_f, 0) + kCols - 1) / kCols) : 0;
+        int64_t total = 0;
+        for (int st = 0; st < L.nstrips; ++st) {
+            int64_t v = sym ? std::min<int64_t>(std::max<int64_t>((int64_t)(st + 1) * kCols - r0, 0), nrows) : nrows;
+            total += v;
+        }
+        L.seg_total = total;
+        const int64_t slots = (int64_t)kCtaSlots * kWarps;
+        int64_t len = (total + slots - 1) / slots;
+        len = std::max<int64_t>((len + kU - 1) / kU * kU, kU);
+        L.seg_len = len;
+        L.seg_warps = (int)((total + len - 1) / len);
+        L.rb = kTileRows; L.stagger = 0; L.persistent = 0; L.nitems = 0;
+        memset(&L.sch, 0, sizeof(L.sch));
+        memset(L.item_base, 0, sizeof(L.item_base));
+        L.sch.count[0] = L.sch.count[1] = 1;
+        L.sch.bounds[0][1] = L.sch.bounds[1][1] = (int)nrows;
+        L.nchunks = (int)((nrows + len - 1) / len) + 1;  // segments a strip can be cut into
+        L.nslots = (size_t)L.nstrips * L.nchunks;
+        L.off_mpart = 0;
+        L.off_gpart = L.off_mpart + align_up(sizeof(double) * kNM * L.nslots, 256);
+        L.off_rpart = align_up(L.off_gpart + sizeof(float) * (size_t)kCols * 3 * L.nslots, 256);
+        L.rpitch = sym ? (int64_t)align_up((size_t)nrows * 3, 32) : 0;
+        L.off_counter = align_up(L.off_rpart + sizeof(float) * (size_t)L.rpitch * L.nstrips, 256);
+        L.total = L.off_counter + 256;
+        return L;
+    }
+    if (variant == 3 || variant == 4) variant = 0;  // same tiles / partial layout as the TMA kernel
     const int unit = variant == 0 ? kTileRows : 8;
     int depth = 0, tail_min = g_tail_min_rows;
     memset(&L.sch, 0, sizeof(L.sch));
-    if (sym && g_rows_per_cta == 0 && g_tail_depth < 0 && nrows > 0) {
+    memset(L.item_base, 0, sizeof(L.item_base));
+    L.nitems = 0;
+    if (L.persistent && nrows > 0) {
+        // items are cheap (the next item's tiles are in flight during the combine) and balanced dynamically: aim at ~12 items per
+        // CTA slot, 128 .. 2048 rows each; no stagger, no tail
+        double work = 0.0;  // strip-rows of this block
+        for (int s = 0; s < L.nstrips; ++s) {
+            const int64_t lim = sym ? std::min<int64_t>(nrows, (int64_t)(s + 1) * kCols - r0) : nrows;
+            if (lim > 0) work += (double)lim;
+        }
+        int64_t rb = (int64_t)(work / kCtaSlots / 12.0);
+        rb = (rb + kTileRows - 1) / kTileRows * kTileRows;
+        if (g_rows_per_cta > 0) rb = (g_rows_per_cta + kTileRows - 1) / kTileRows * kTileRows;
+        rb = std::max<int64_t>(2 * kTileRows, std::min<int64_t>(rb, 2048));
+        while ((nrows + rb - 1) / rb > kMaxChunks - 20) rb += kTileRows;
+        L.rb = (int)rb;
+        L.stagger = 0;
+    } else if (sym && g_rows_per_cta == 0 && g_tail_depth < 0 && nrows > 0) {
         // equal chunks, no explicit tail (the triangle tapers by itself): pick the chunk length by simulation
         static const int cand0[] = {256, 384, 512, 640, 768, 1024, 1280, 1536, 2048, 3072, 4096};
         static const int cand1[] = {256, 384, 512, 768, 1024};  // the implicit-target kernel stages a chunk of x_i in 48 KB of shared memory
@@ -1176,7 +1595,17 @@ Layout make_layout_uncached(int64_t n, int64_t r0, int64_t r1, int variant, bool
     L.off_gpart = L.off_mpart + align_up(sizeof(double) * kNM * L.nslots, 256);
     L.off_rpart = align_up(L.off_gpart + sizeof(float) * (size_t)kCols * 3 * L.nslots, 256);
     L.rpitch = sym ? (int64_t)align_up((size_t)(nrows > 0 ? nrows : 1) * 3, 32) : 0;
-    L.total = L.off_rpart + sizeof(float) * (size_t)L.rpitch * L.nstrips;
+    L.off_counter = align_up(L.off_rpart + sizeof(float) * (size_t)L.rpitch * L.nstrips, 256);
+    L.total = L.off_counter + 256;
+    if (L.persistent) {
+        for (int c = 0; c < L.sch.count[0]; ++c) {
+            int first = 0;
+            if (sym) first = (int)std::max<int64_t>(0, (r0 + L.sch.bounds[0][c]) / kCols);  // strips left of it lie below the diagonal
+            if (first > L.nstrips) first = L.nstrips;
+            L.item_base[c + 1] = L.item_base[c] + (L.nstrips - first);
+        }
+        L.nitems = L.item_base[L.sch.count[0]];
+    }
     return L;
 }
 
@@ -1278,10 +1707,63 @@ cudaError_t launch_tma(const CUtensorMap& map, const Params& P, dim3 grid, cudaS
     return cudaLaunchKernelEx(&cfg, pairloss_tma_kernel<MODE, ROWS>, map, P);
 }
 
+template <uint32_t MODE, bool ROWS>
+cudaError_t launch_persist(const CUtensorMap& map, const Params& P, cudaStream_t stream) {
+    static std::atomic<uint64_t> attr_set{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (dev >= 64 || !(attr_set.load(std::memory_order_relaxed) & bit)) {
+        cudaError_t e = cudaFuncSetAttribute(pairloss_tma_persist_kernel<MODE, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmem);
+        if (e != cudaSuccess) return e;
+        attr_set.fetch_or(bit, std::memory_order_relaxed);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min(P.nitems, kCtaSlots));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kPersistSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, pairloss_tma_persist_kernel<MODE, ROWS>, map, P);
+}
+
+template <uint32_t MODE, bool ROWS>
+cudaError_t launch_warp(const CUtensorMap& map, const Params& P, int nwarps, cudaStream_t stream) {
+    static std::atomic<uint64_t> attr_set{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (dev >= 64 || !(attr_set.load(std::memory_order_relaxed) & bit)) {
+        cudaError_t e = cudaFuncSetAttribute(pairloss_tma_warp_kernel<MODE, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
+        if (e != cudaSuccess) return e;
+        attr_set.fetch_or(bit, std::memory_order_relaxed);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((nwarps + kWarps - 1) / kWarps));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kTmaSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, pairloss_tma_warp_kernel<MODE, ROWS>, map, P);
+}
+
 template <uint32_t MODE>
 cudaError_t launch_mode(int variant, const CUtensorMap& map, const Params& P, dim3 grid, cudaStream_t stream) {
     cudaError_t e;
-    if (variant == 0) {
+    if (variant == 4) {
+        const int nwarps = (int)((P.seg_total + P.seg_len - 1) / P.seg_len);
+        e = P.upper ? launch_warp<MODE, true>(map, P, nwarps, stream) : launch_warp<MODE, false>(map, P, nwarps, stream);
+    } else if (variant == 3) {
+        e = P.upper ? launch_persist<MODE, true>(map, P, stream) : launch_persist<MODE, false>(map, P, stream);
+    } else if (variant == 0) {
         e = P.upper ? launch_tma<MODE, true>(map, P, grid, stream) : launch_tma<MODE, false>(map, P, grid, stream);
     } else {
         const size_t smem = (sizeof(float4) + sizeof(float2)) * (size_t)P.rb;
@@ -1308,8 +1790,8 @@ extern "C" int hicgat_pairloss_set_tuning(int rows_per_cta, int variant) {
         set_error("hicgat_pairloss_set_tuning: rows_per_cta must be 0 or a multiple of 8 in [8,4096]");
         return HICGAT_ERR_INVALID;
     }
-    if (variant < 0 || variant > 2) {
-        set_error("hicgat_pairloss_set_tuning: variant must be 0 (TMA ring), 1 (per-lane loads) or 2 (TMA ring, unstaggered chunks)");
+    if (variant < 0 || variant > 4) {
+        set_error("hicgat_pairloss_set_tuning: variant must be 0 (TMA ring), 1 (per-lane loads), 2 (TMA ring, unstaggered chunks), 3 (persistent TMA ring) or 4 (static warp partition)");
         return HICGAT_ERR_INVALID;
     }
     g_rows_per_cta = rows_per_cta;
@@ -1368,15 +1850,16 @@ extern "C" double hicgat_pairloss_estimate_cost(int64_t n, int64_t r0, int64_t r
 extern "C" size_t hicgat_pairloss_workspace_bytes(int64_t n, int64_t r0, int64_t r1) {
     if (n <= 0 || r0 < 0 || r1 < r0 || r1 > n) return 0;
     // for the CURRENT tuning (re-query after set_tuning); covers either variant
-    const size_t a = make_layout(n, r0, r1, 0).total, b = make_layout(n, r0, r1, 1).total;
-    return a > b ? a : b;
+    const size_t a = make_layout(n, r0, r1, 0).total, b = make_layout(n, r0, r1, 1).total, c = make_layout(n, r0, r1, 3).total, d = make_layout(n, r0, r1, 4).total;
+    return std::max(std::max(a, d), std::max(b, c));
 }
 
 extern "C" size_t hicgat_pairloss_workspace_bytes_mode(int64_t n, int64_t r0, int64_t r1, uint32_t mode) {
     if (n <= 0 || r0 < 0 || r1 < r0 || r1 > n) return 0;
     const bool sym = (mode & HICGAT_PAIR_SYMMETRIC) != 0;
-    const size_t a = make_layout(n, r0, r1, 0, sym).total, b = make_layout(n, r0, r1, 1).total;
-    return a > b ? a : b;
+    const size_t a = make_layout(n, r0, r1, 0, sym).total, b = make_layout(n, r0, r1, 1).total, c = make_layout(n, r0, r1, 3, sym).total,
+                 d = make_layout(n, r0, r1, 4, sym).total;
+    return std::max(std::max(a, d), std::max(b, c));
 }
 
 static int pairloss_impl(const float* coords, const float* target, int64_t pitch, int64_t n,
@@ -1390,7 +1873,8 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     HICGAT_REQUIRE(pitch >= n && (pitch % 4) == 0, "hicgat_pairloss_fwd_bwd: pitch %lld must be >= n and a multiple of 4", (long long)pitch);
     HICGAT_REQUIRE(aligned16(target), "hicgat_pairloss_fwd_bwd: target must be 16-byte aligned");  // NULL passes
     HICGAT_REQUIRE((mode & ~63u) == 0, "hicgat_pairloss_fwd_bwd: unknown mode bits 0x%x", mode);
-    mode &= ~HICGAT_PAIR_WS_CLEAN;  // accepted for ABI compatibility; the workspace holds no state between calls
+    const bool ws_clean = (mode & HICGAT_PAIR_WS_CLEAN) != 0;  // the persistent variant keeps ONE item counter in the workspace (left at zero by every call)
+    mode &= ~HICGAT_PAIR_WS_CLEAN;
     bool sym = (mode & HICGAT_PAIR_SYMMETRIC) != 0;
     mode &= ~HICGAT_PAIR_SYMMETRIC;
     if (mode & HICGAT_PAIR_MOMENTS) mode &= ~HICGAT_PAIR_MOMENTS_D;          // full moments include the light set
@@ -1400,8 +1884,8 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     HICGAT_REQUIRE(!(mode & 3u) || grad || grad64, "hicgat_pairloss_fwd_bwd: grad is NULL but a gradient mode is set");
     int variant = g_variant;
     CUtensorMap map;
-    if (variant == 0 && r1 > r0 && !make_target_map(&map, target, pitch, n, r1 - r0)) variant = 1;
-    if (variant != 0) sym = false;  // the per-lane-load variant streams the whole row block (A/B path; same results)
+    if (variant != 1 && r1 > r0 && !make_target_map(&map, target, pitch, n, r1 - r0)) variant = 1;
+    if (variant == 1) sym = false;  // the per-lane-load variant streams the whole row block (A/B path; same results)
     const Layout L = make_layout(n, r0, r1, variant, sym);
     if (workspace_bytes < L.total) {
         set_error("hicgat_pairloss_fwd_bwd: workspace %zu < required %zu", workspace_bytes, L.total);
@@ -1422,6 +1906,14 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
     P.mpart = reinterpret_cast<double*>(ws + L.off_mpart);
     P.gpart = reinterpret_cast<float*>(ws + L.off_gpart);
     P.upper = sym ? 1 : 0; P.rpitch = L.rpitch; P.rpart = reinterpret_cast<float*>(ws + L.off_rpart);
+    P.work_counter = nullptr; P.nitems = 0;
+    P.seg_len = L.seg_len; P.seg_total = L.seg_total; P.seg_sa = L.seg_sa; P.seg_sb = L.seg_sb; P.seg_f = L.seg_f;
+    if (L.persistent) {
+        P.work_counter = reinterpret_cast<unsigned*>(ws + L.off_counter);
+        P.nitems = L.nitems;
+        memcpy(P.item_base, L.item_base, sizeof(P.item_base));
+        if (!ws_clean) HICGAT_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned), stream));
+    }
     dim3 grid(L.nstrips, L.nchunks);
     cudaError_t err = cudaSuccess;
     switch (mode) {
@@ -1534,6 +2026,8 @@ static int pairloss_sparse_impl(const float* coords, const int32_t* rowptr, cons
     P.mpart = reinterpret_cast<double*>(ws + L.dense.off_mpart);
     P.gpart = reinterpret_cast<float*>(ws + L.dense.off_gpart);
     P.upper = sym ? 1 : 0; P.rpitch = L.dense.rpitch; P.rpart = reinterpret_cast<float*>(ws + L.dense.off_rpart);
+    P.work_counter = nullptr; P.nitems = 0;
+    P.seg_len = 0; P.seg_total = 0; P.seg_sa = P.seg_sb = P.seg_f = 0;
     dim3 grid(L.dense.nstrips, L.dense.nchunks);
     double* part = reinterpret_cast<double*>(ws + L.off_part);
     unsigned* counter = reinterpret_cast<unsigned*>(ws + L.off_counter);

@@ -88,10 +88,10 @@ HICGAT_API int hicgat_memcpy2d_h2d_async(void* dst_device, size_t dst_pitch_byte
  * as 0).  sum t and sum t^2 are constants of the target: take them ONCE from a
  * HICGAT_PAIR_MOMENTS launch.  Implied by HICGAT_PAIR_MOMENTS. */
 #define HICGAT_PAIR_MOMENTS_D 8u
-/* Accepted and ignored by hicgat_pairloss_fwd_bwd since the cross-CTA sums moved into their own kernel (the
- * dense-target workspace holds no state between calls).  hicgat_pairloss_sparse_fwd_bwd still keeps ONE
- * ticket counter for its CSR correction pass: with this bit the caller promises it is zero (every
- * successful call leaves it zeroed) and the reset memset is skipped. */
+/* The workspace keeps ONE 32-bit counter between calls (the item queue of the persistent loss kernel, the ticket of
+ * hicgat_pairloss_sparse_fwd_bwd's CSR correction pass): with this bit the caller promises it is zero -- a workspace
+ * that was zero-filled once and used for nothing else qualifies: every successful call leaves the counter at zero --
+ * and the reset memset is skipped. */
 #define HICGAT_PAIR_WS_CLEAN 16u
 /* The caller has VERIFIED t_ij == t_ji (hicgat_asymmetry_f32 == 0, or a target built from a symmetric map): only the
  * upper triangle (column >= row) of rows [r0,r1) is streamed -- 2 B per ordered pair instead of 4 -- and every
@@ -122,8 +122,11 @@ HICGAT_API int hicgat_pairloss_fwd_bwd_packed(const float* coords, const float* 
                                    float c_l1, double* packed, void* workspace,
                                    size_t workspace_bytes, hicgat_stream_t stream);
 /* Tuning hook (bench/tests): rows per CTA row-chunk (0 = library default) and kernel variant:
- * 0 = TMA tile ring (cp.async.bulk.tensor + mbarrier, default), 1 = per-lane streaming loads,
- * 2 = TMA tile ring without the half-chunk stagger of the second CTA slot (A/B only). */
+ * 0 = TMA tile ring (cp.async.bulk.tensor + mbarrier), one CTA per (strip, row chunk); 1 = per-lane streaming loads;
+ * 2 = TMA tile ring without the half-chunk stagger of the second CTA slot (A/B only); 3 = the same ring in PERSISTENT CTAs that
+ * pull (chunk, strip) items from an atomic queue and prefetch the next item's tiles across the item boundary; 4 = static warp
+ * partition: the block's (strip, row) work is cut into equal runs, one per resident warp (no dispatch, no CTA-level
+ * synchronisation, no tail). */
 HICGAT_API int hicgat_pairloss_set_tuning(int rows_per_cta, int variant);
 /* Tuning hook (bench/tests): shape of the row-chunk schedule.  Every column strip is cut into chunks of
  * about rows_per_cta rows followed by `tail_depth` chunks that halve each time (down to tail_min_rows), so

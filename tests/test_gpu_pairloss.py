@@ -140,7 +140,7 @@ def test_tuning_variants_agree():
     tgt = hg.WishTarget.from_dense(truth)
     ref = None
     try:
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3, 4):
             for rb in (0, 8, 64, 256, 1024):
                 N.set_pairloss_tuning(rb, variant)
                 for mode in ("mse_moments_full", "contrastive"):
@@ -154,7 +154,7 @@ def test_tuning_variants_agree():
         N.set_pairloss_tuning(0, 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("n,r0,r1,rb", [(130, 0, 130, 0), (777, 3, 500, 0), (1000, 999, 1000, 0), (513, 64, 449, 0), (19500, 100, 1000, 128), (19300, 0, 700, 64),
                                         (40000, 5, 205, 0), (80000, 17, 60, 0)])
 def test_row_blocks_any_alignment_both_variants(variant, n, r0, r1, rb):
@@ -403,8 +403,9 @@ def test_upper_triangle_kernel_matches_oracle(n, mode):
     assert torch.equal(g, g3) and torch.equal(moments, moments3)
 
 
+@pytest.mark.parametrize("variant", [0, 3, 4])
 @pytest.mark.parametrize("n,cuts,rb", [(777, [0, 200, 200, 601, 777], 0), (1000, [0, 999, 1000], 0), (513, [0, 64, 449, 513], 0), (3001, [0, 5, 1000, 1003, 3001], 64)])
-def test_upper_triangle_row_blocks_sum_to_full(n, cuts, rb):
+def test_upper_triangle_row_blocks_sum_to_full(n, cuts, rb, variant):
     """Row blocks of any alignment (incl. empty ones and blocks that start inside a column strip): per block, f64 torch evaluation
     of the block's share (t_ii^2 + 2 sum_{j>i} e^2; column- plus row-side gradient of the pairs i in block, j > i)."""
     import hic_gnn_b200 as hg
@@ -415,7 +416,7 @@ def test_upper_triangle_row_blocks_sum_to_full(n, cuts, rb):
     c = coords.double()
     g = torch.Generator().manual_seed(n)
     try:
-        N.set_pairloss_tuning(rb, 0)
+        N.set_pairloss_tuning(rb, variant)  # 3 = persistent CTAs with an item queue, 4 = static warp partition
         for r0, r1 in zip(cuts[:-1], cuts[1:]):
             # only the upper part of the block's rows matters: the lower triangle holds garbage on purpose
             rows = torch.rand(r1 - r0, n, generator=g, dtype=torch.float64).float().double()
@@ -445,8 +446,9 @@ def test_upper_triangle_row_blocks_sum_to_full(n, cuts, rb):
         N.set_pairloss_tuning(0, 0)
 
 
+@pytest.mark.parametrize("variant", [0, 3, 4])
 @pytest.mark.parametrize("n,cuts,rb", [(19500, [0, 100, 6016, 19500], 0), (19300, [0, 700, 19300], 128), (30000, [0, 30000], 0)])
-def test_upper_triangle_large_maps_match_full_matrix_kernel(n, cuts, rb):
+def test_upper_triangle_large_maps_match_full_matrix_kernel(n, cuts, rb, variant):
     """More than 148 column strips (staggered chunk tables, several waves): the upper-triangle kernel over row blocks of a
     symmetric matrix must reproduce the full-matrix kernel's result on the same matrix (1e-6 moments / 1e-5 gradient), and the
     implicit-target kernels (upper and full) must agree with each other."""
@@ -464,7 +466,7 @@ def test_upper_triangle_large_maps_match_full_matrix_kernel(n, cuts, rb):
     m_ref, g_ref = ops.pairloss_raw(coords, full, mode, 4.0 / n**2, 0.0)
     m_sum, g_sum = torch.zeros_like(m_ref), torch.zeros_like(g_ref)
     try:
-        N.set_pairloss_tuning(rb, 0)
+        N.set_pairloss_tuning(rb, variant)
         for r0, r1 in zip(cuts[:-1], cuts[1:]):
             blk = hg.WishTarget(full.data[r0:r1], n, r0, r1, symmetric=True)
             m, gr = ops.pairloss_raw(coords, blk, mode, 4.0 / n**2, 0.0)
