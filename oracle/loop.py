@@ -77,10 +77,11 @@ def train(
             extra = {}
         else:
             raise ValueError(mode)
-        diff = abs(old - float(total))
+        value = float(total.detach())
+        diff = abs(old - value)
         total.backward()
         optimizer.step()
-        old = float(total)
+        old = value
         hist.append(old)
         extras.append(extra)
         step += 1
