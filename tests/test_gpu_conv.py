@@ -549,7 +549,7 @@ def test_c3_size_full_train_step_against_oracle():
     with torch.no_grad():
         coords_g = gm.get_model(gdata.x.float(), gdata.edge_index)
     assert rel_err(coords_g, coords_o) < 1e-4   # near-collapsed initial structure: coordinates are differences of O(1) activations
-    assert abs(float(lg.detach()) - float(lo64)) / abs(float(lo64)) < TOL
+    assert abs(float(lg.detach()) - float(lo64.detach())) / abs(float(lo64.detach())) < TOL
     from scipy.stats import pearsonr
 
     c64 = coords_o.detach().double()
