@@ -557,7 +557,7 @@ def test_c3_size_full_train_step_against_oracle():
     iu = torch.triu_indices(n, n, 1)
     r64 = pearsonr(truth[iu[0], iu[1]].numpy(), d64[iu[0], iu[1]].numpy())[0]
     assert abs(float(pearson_from_moments(moments, n * (n - 1) / 2)) - r64) < 1e-6
-    total64 = float(lo64) + min(1.0, 0.1 + 1.0 / (float(lo64) + 1e-6)) * (1.0 - r64)
+    total64 = float(lo64.detach()) + min(1.0, 0.1 + 1.0 / (float(lo64.detach()) + 1e-6)) * (1.0 - r64)
     assert abs(float(total) - total64) / abs(total64) < TOL
     errs = []
     for name, p in gm.named_parameters():
