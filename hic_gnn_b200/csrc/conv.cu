@@ -100,13 +100,13 @@ __global__ void __launch_bounds__(256) gat_logit_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------ GAT forward
-template <int H, int Q>
-__global__ void __launch_bounds__(256) gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+template <int H, int Q, int W>
+__global__ void __launch_bounds__(W * 32) gat_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                       const float* __restrict__ xl, const float* __restrict__ a_src,
                                                       const float* __restrict__ a_dst, const float* __restrict__ bias,
                                                       float slope, int n, float* __restrict__ alpha, float* __restrict__ out) {
     constexpr int F = Q * 128, QH = Q / H;
-    const int i = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int i = blockIdx.x * W + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= n) return;
     const int rs = rowptr[i], re = rowptr[i + 1];
     float adst[H], m[H], s[H];
@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(256) gat_bwd_rowdot_kernel(const float* __rest
     }
 }
 
-template <int H, int Q>
-__global__ void __launch_bounds__(256, 2) gat_bwd_fused_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+template <int H, int Q, int W>
+__global__ void __launch_bounds__(W * 32, 16 / W) gat_bwd_fused_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                                const int32_t* __restrict__ perm, const float* __restrict__ xl,
                                                                const float* __restrict__ a_src, const float* __restrict__ a_dst,
                                                                const float* __restrict__ alpha, const float* __restrict__ rowdot,
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(256, 2) gat_bwd_fused_kernel(const int32_t* __
                                                                int n, float* __restrict__ dz, float* __restrict__ d_a_src,
                                                                float* __restrict__ dxl) {
     constexpr int F = Q * 128, QH = Q / H;
-    const int jn = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int jn = blockIdx.x * W + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (jn >= n) return;
     const int rs = rowptr[jn], re = rowptr[jn + 1];
     float4 x[Q], acc[Q];
@@ -619,6 +619,9 @@ bool supported(int H, int C) {
     return (H == 1 || H == 2 || H == 4) && C % 128 == 0 && (F == 128 || F == 256 || F == 512 || F == 1024);
 }
 
+// warps (= consecutive rows) per CTA of the two gather kernels (gat_fwd / gat_bwd_fused): 8 or 16, see hicgat_gat_set_tuning
+int g_gather_warps = 8;
+
 #define HICGAT_DISPATCH_HQ(H, C, CALL)                              \
     do {                                                            \
         const int q__ = (H) * (C) / 128;                            \
@@ -655,6 +658,12 @@ extern "C" int hicgat_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     return HICGAT_OK;
 }
 
+extern "C" int hicgat_gat_set_tuning(int rows_per_cta) {
+    HICGAT_REQUIRE(rows_per_cta == 8 || rows_per_cta == 16, "hicgat_gat_set_tuning: rows_per_cta must be 8 or 16");
+    g_gather_warps = rows_per_cta;
+    return HICGAT_OK;
+}
+
 extern "C" int hicgat_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n, int heads, int channels, const float* xl,
                               const float* att_l, const float* att_r, const float* bias, float slope, float* a_src,
                               float* a_dst, float* alpha, float* out, hicgat_stream_t stream_) {
@@ -668,7 +677,9 @@ extern "C" int hicgat_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t
     HICGAT_DISPATCH_HQ(heads, channels, CALL_LOGIT);
 #undef CALL_LOGIT
     HICGAT_CHECK_LAUNCH("gat_logit_kernel");
-#define CALL_FWD(H, Q) gat_fwd_kernel<H, Q><<<grid, 256, 0, stream>>>(rowptr, col, xl, a_src, a_dst, bias, slope, (int)n, alpha, out)
+#define CALL_FWD(H, Q)                                                                                                                  \
+    if (g_gather_warps == 16) gat_fwd_kernel<H, Q, 16><<<(unsigned)((n + 15) / 16), 512, 0, stream>>>(rowptr, col, xl, a_src, a_dst, bias, slope, (int)n, alpha, out); \
+    else gat_fwd_kernel<H, Q, 8><<<grid, 256, 0, stream>>>(rowptr, col, xl, a_src, a_dst, bias, slope, (int)n, alpha, out)
     HICGAT_DISPATCH_HQ(heads, channels, CALL_FWD);
 #undef CALL_FWD
     HICGAT_CHECK_LAUNCH("gat_fwd_kernel");
@@ -766,7 +777,9 @@ extern "C" int hicgat_gat_bwd_fused(const int32_t* rowptr, const int32_t* col, c
     HICGAT_DISPATCH_HQ(heads, channels, CALL_ROWDOT);
 #undef CALL_ROWDOT
     HICGAT_CHECK_LAUNCH("gat_bwd_rowdot_kernel");
-#define CALL_FUSED(H, Q) gat_bwd_fused_kernel<H, Q><<<grid, 256, 0, stream>>>(rowptr, col, perm, xl, a_src, a_dst, alpha, rowdot, gout, att_l, slope, (int)n, dz, dsrc, dxl)
+#define CALL_FUSED(H, Q)                                                                                                                \
+    if (g_gather_warps == 16) gat_bwd_fused_kernel<H, Q, 16><<<(unsigned)((n + 15) / 16), 512, 0, stream>>>(rowptr, col, perm, xl, a_src, a_dst, alpha, rowdot, gout, att_l, slope, (int)n, dz, dsrc, dxl); \
+    else gat_bwd_fused_kernel<H, Q, 8><<<grid, 256, 0, stream>>>(rowptr, col, perm, xl, a_src, a_dst, alpha, rowdot, gout, att_l, slope, (int)n, dz, dsrc, dxl)
     HICGAT_DISPATCH_HQ(heads, channels, CALL_FUSED);
 #undef CALL_FUSED
     HICGAT_CHECK_LAUNCH("gat_bwd_fused_kernel");

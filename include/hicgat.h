@@ -345,6 +345,9 @@ HICGAT_API int hicgat_csr_transpose_perm(const int32_t* rowptr, const int32_t* c
  *         out = softmax_row(leaky_relu(a_src[j] + a_dst[i], slope)) @ xl  + bias
  *   bwd : given g = dL/dout: dxl [n,H*C], datt_l/datt_r [H*C] (+=), dbias [H*C]
  * ---------------------------------------------------------------------------------- */
+/* Process-wide tuning of the two gather kernels (gat_fwd, gat_bwd_fused): consecutive rows (= warps) per CTA, 8 or 16.
+ * Consecutive rows of a Hi-C map share neighbours, so one CTA's rows re-use each other's gathered xl rows in L1. */
+HICGAT_API int hicgat_gat_set_tuning(int rows_per_cta);
 HICGAT_API int hicgat_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n, int heads, int channels,
                    const float* xl, const float* att_l, const float* att_r, const float* bias,
                    float slope, float* a_src, float* a_dst, float* alpha, float* out,
