@@ -11,6 +11,7 @@ TOL_GRAD = 1e-5  # north_star tolerance for gradients
 
 
 def rel_err(a, b):
+    a, b = a.detach(), b.detach()
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp(min=1e-300))
 
 
