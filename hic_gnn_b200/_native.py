@@ -55,7 +55,7 @@ SIGNATURES = {
     "hicgat_sage_norm_values": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
     "hicgat_spmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p]),
     "hicgat_csr_transpose_perm": (C.c_int, [_p, _p, _i64, _p, _p]),
-    "hicgat_gat_set_tuning": (C.c_int, [_i32]),
+    "hicgat_gat_set_tuning": (C.c_int, [_i32, _i32]),
     "hicgat_gat_fwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),
     "hicgat_gat_bwd_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "hicgat_gat_logits": (C.c_int, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),

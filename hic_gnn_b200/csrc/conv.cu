@@ -9,6 +9,8 @@
 // Nothing is materialised per edge except alpha / dz ([nnz, H] floats); PyG materialises
 // [nnz, H, C].  Features are read as float4: lane l owns channels q*128 + 4l .. +3 of each
 // 128-wide chunk q (Q = H*C/128 chunks), so one chunk always belongs to a single head.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace hicgat {
@@ -621,6 +623,30 @@ bool supported(int H, int C) {
 
 // warps (= consecutive rows) per CTA of the two gather kernels (gat_fwd / gat_bwd_fused): 8 or 16, see hicgat_gat_set_tuning
 int g_gather_warps = 8;
+// bytes of L2 set aside for the GATHERED matrix (xl in the forward, gout in the backward): 0 = off
+size_t g_l2_persist_bytes = 0;
+
+// Launch of a gather kernel; with g_l2_persist_bytes > 0 the gathered matrix gets a persisting access-policy window (launch
+// attribute, nothing is changed on the caller's stream), so that the streamed col / alpha / output traffic does not evict it.
+template <typename... KArgs, typename... Args>
+void launch_gather(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, const void* gathered, size_t bytes, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (g_l2_persist_bytes > 0) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(gathered);
+        attr[0].val.accessPolicyWindow.num_bytes = bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = bytes <= g_l2_persist_bytes ? 1.0f : (float)((double)g_l2_persist_bytes / (double)bytes);
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #define HICGAT_DISPATCH_HQ(H, C, CALL)                              \
     do {                                                            \
@@ -658,9 +684,24 @@ extern "C" int hicgat_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     return HICGAT_OK;
 }
 
-extern "C" int hicgat_gat_set_tuning(int rows_per_cta) {
+extern "C" int hicgat_gat_set_tuning(int rows_per_cta, int l2_persist_mb) {
     HICGAT_REQUIRE(rows_per_cta == 8 || rows_per_cta == 16, "hicgat_gat_set_tuning: rows_per_cta must be 8 or 16");
+    HICGAT_REQUIRE(l2_persist_mb >= 0, "hicgat_gat_set_tuning: l2_persist_mb must be >= 0");
+    size_t bytes = (size_t)l2_persist_mb << 20;
+    if (bytes > 0) {  // device-wide carve-out of L2 for persisting lines (current device), capped by what the device allows
+        int dev = 0, max_persist = 0, max_window = 0;
+        HICGAT_CUDA(cudaGetDevice(&dev));
+        HICGAT_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+        HICGAT_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+        bytes = std::min(bytes, (size_t)max_persist);
+        HICGAT_REQUIRE(bytes > 0 && max_window > 0, "hicgat_gat_set_tuning: the device has no persisting L2 carve-out");
+        HICGAT_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+    } else if (g_l2_persist_bytes > 0) {
+        HICGAT_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
+        HICGAT_CUDA(cudaCtxResetPersistingL2Cache());
+    }
     g_gather_warps = rows_per_cta;
+    g_l2_persist_bytes = bytes;
     return HICGAT_OK;
 }
 
@@ -677,9 +718,10 @@ extern "C" int hicgat_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t
     HICGAT_DISPATCH_HQ(heads, channels, CALL_LOGIT);
 #undef CALL_LOGIT
     HICGAT_CHECK_LAUNCH("gat_logit_kernel");
+    const size_t gathered_bytes = (size_t)n * heads * channels * sizeof(float);
 #define CALL_FWD(H, Q)                                                                                                                  \
-    if (g_gather_warps == 16) gat_fwd_kernel<H, Q, 16><<<(unsigned)((n + 15) / 16), 512, 0, stream>>>(rowptr, col, xl, a_src, a_dst, bias, slope, (int)n, alpha, out); \
-    else gat_fwd_kernel<H, Q, 8><<<grid, 256, 0, stream>>>(rowptr, col, xl, a_src, a_dst, bias, slope, (int)n, alpha, out)
+    if (g_gather_warps == 16) launch_gather(gat_fwd_kernel<H, Q, 16>, (unsigned)((n + 15) / 16), 512, stream, xl, gathered_bytes, rowptr, col, xl, a_src, a_dst, bias, slope, (int)n, alpha, out); \
+    else launch_gather(gat_fwd_kernel<H, Q, 8>, grid, 256, stream, xl, gathered_bytes, rowptr, col, xl, a_src, a_dst, bias, slope, (int)n, alpha, out)
     HICGAT_DISPATCH_HQ(heads, channels, CALL_FWD);
 #undef CALL_FWD
     HICGAT_CHECK_LAUNCH("gat_fwd_kernel");
@@ -777,9 +819,10 @@ extern "C" int hicgat_gat_bwd_fused(const int32_t* rowptr, const int32_t* col, c
     HICGAT_DISPATCH_HQ(heads, channels, CALL_ROWDOT);
 #undef CALL_ROWDOT
     HICGAT_CHECK_LAUNCH("gat_bwd_rowdot_kernel");
+    const size_t gathered_bytes = (size_t)n * heads * channels * sizeof(float);
 #define CALL_FUSED(H, Q)                                                                                                                \
-    if (g_gather_warps == 16) gat_bwd_fused_kernel<H, Q, 16><<<(unsigned)((n + 15) / 16), 512, 0, stream>>>(rowptr, col, perm, xl, a_src, a_dst, alpha, rowdot, gout, att_l, slope, (int)n, dz, dsrc, dxl); \
-    else gat_bwd_fused_kernel<H, Q, 8><<<grid, 256, 0, stream>>>(rowptr, col, perm, xl, a_src, a_dst, alpha, rowdot, gout, att_l, slope, (int)n, dz, dsrc, dxl)
+    if (g_gather_warps == 16) launch_gather(gat_bwd_fused_kernel<H, Q, 16>, (unsigned)((n + 15) / 16), 512, stream, gout, gathered_bytes, rowptr, col, perm, xl, a_src, a_dst, alpha, rowdot, gout, att_l, slope, (int)n, dz, dsrc, dxl); \
+    else launch_gather(gat_bwd_fused_kernel<H, Q, 8>, grid, 256, stream, gout, gathered_bytes, rowptr, col, perm, xl, a_src, a_dst, alpha, rowdot, gout, att_l, slope, (int)n, dz, dsrc, dxl)
     HICGAT_DISPATCH_HQ(heads, channels, CALL_FUSED);
 #undef CALL_FUSED
     HICGAT_CHECK_LAUNCH("gat_bwd_fused_kernel");

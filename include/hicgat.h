@@ -345,9 +345,13 @@ HICGAT_API int hicgat_csr_transpose_perm(const int32_t* rowptr, const int32_t* c
  *         out = softmax_row(leaky_relu(a_src[j] + a_dst[i], slope)) @ xl  + bias
  *   bwd : given g = dL/dout: dxl [n,H*C], datt_l/datt_r [H*C] (+=), dbias [H*C]
  * ---------------------------------------------------------------------------------- */
-/* Process-wide tuning of the two gather kernels (gat_fwd, gat_bwd_fused): consecutive rows (= warps) per CTA, 8 or 16.
- * Consecutive rows of a Hi-C map share neighbours, so one CTA's rows re-use each other's gathered xl rows in L1. */
-HICGAT_API int hicgat_gat_set_tuning(int rows_per_cta);
+/* Process-wide tuning of the two gather kernels (gat_fwd, gat_bwd_fused).
+ * rows_per_cta: consecutive rows (= warps) per CTA, 8 (default) or 16 -- consecutive rows of a Hi-C map share neighbours,
+ *   so one CTA's rows re-use each other's gathered rows in L1.
+ * l2_persist_mb: > 0 sets aside that much L2 of the CURRENT device (cudaLimitPersistingL2CacheSize, capped by the device
+ *   maximum) and launches the gather kernels with a persisting access-policy window over the gathered matrix (xl in the
+ *   forward, dL/dout in the backward); 0 (default) = off and gives the carve-out back. */
+HICGAT_API int hicgat_gat_set_tuning(int rows_per_cta, int l2_persist_mb);
 HICGAT_API int hicgat_gat_fwd(const int32_t* rowptr, const int32_t* col, int64_t n, int heads, int channels,
                    const float* xl, const float* att_l, const float* att_r, const float* bias,
                    float slope, float* a_src, float* a_dst, float* alpha, float* out,

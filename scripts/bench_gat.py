@@ -29,7 +29,7 @@ def timed(fn, reps=10, warm=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workloads", default="c5,c4")
-    ap.add_argument("--rows", default="8,16")
+    ap.add_argument("--rows", default="8,16", help="rows_per_cta[:l2_persist_mb] variants")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     import bench
@@ -50,8 +50,9 @@ def main():
         gout = torch.randn(n, 512, device="cuda", generator=g)
         entry = {"n": n, "edges_with_self_loops": int(graph.with_self_loops()[1].numel())}
         ref = None
-        for rows in [int(r) for r in args.rows.split(",")]:
-            N.check(N.lib().hicgat_gat_set_tuning(rows), "hicgat_gat_set_tuning")
+        for spec in args.rows.split(","):
+            rows, l2mb = (int(v) for v in (spec.split(":") + ["0"])[:2])
+            N.check(N.lib().hicgat_gat_set_tuning(rows, l2mb), "hicgat_gat_set_tuning")
             fwd = lambda: layers._GatAttend.apply(xl, conv.att_l, conv.att_r, conv.bias, graph, 2, 256, 0.2)
             out = fwd()
             t_f = timed(lambda: fwd())
@@ -62,8 +63,8 @@ def main():
                 same = True
             else:  # the row -> warp mapping does not change any summation order: bit-identical
                 same = bool(torch.equal(out, ref[0])) and all(bool(torch.equal(a, b)) for a, b in zip(grads, ref[1]))
-            entry[f"rows{rows}"] = {"fwd_ms": round(t_f, 4), "fwd_bwd_ms": round(t_fb, 4), "bwd_ms": round(t_fb - t_f, 4), "bit_identical_to_first": same}
-        N.check(N.lib().hicgat_gat_set_tuning(8), "hicgat_gat_set_tuning")
+            entry[f"rows{rows}" + (f"_l2persist{l2mb}mb" if l2mb else "")] = {"fwd_ms": round(t_f, 4), "fwd_bwd_ms": round(t_fb, 4), "bwd_ms": round(t_fb - t_f, 4), "bit_identical_to_first": same}
+        N.check(N.lib().hicgat_gat_set_tuning(8, 0), "hicgat_gat_set_tuning")
         res[name] = entry
         print(name, json.dumps(entry), flush=True)
         del graph, xl, gout
