@@ -118,6 +118,35 @@ def test_gat_csr_backward_one_pass_matches_two_pass(monkeypatch, n, density):
         assert rel_err(a, b) < TOL, name
 
 
+@pytest.mark.parametrize("rows,l2_mb", [(16, 0), (8, 16), (16, 16)])
+def test_gat_gather_tuning_is_bit_identical(rows, l2_mb):
+    """``hicgat_gat_set_tuning``: 16 rows per CTA and the L2 persisting window change scheduling / caching only -- no summation
+    order -- so forward and every gradient are bit-identical with the default launch.  Bad arguments are refused."""
+    from hic_gnn_b200 import _native as N, layers as glayers
+
+    n = 1003  # not a multiple of 8 or 16: the last CTA is ragged
+    x, _, gdata, oc = _gat_case(n, 0.1, min_kink_gap=0.0)
+    gc = glayers.GATConv(512, 256, heads=2).cuda()
+    gc.path = "csr"
+    gc.load_state_dict(oc.state_dict())
+    w = torch.randn(n, 512, generator=torch.Generator().manual_seed(1)).cuda()
+
+    def run():
+        xg = x.cuda().requires_grad_(True)
+        yg = gc(xg, gdata.edge_index)
+        return [yg.detach()] + list(torch.autograd.grad((yg * w).sum(), [xg, gc.lin_l.weight, gc.att_l, gc.att_r, gc.bias]))
+
+    want = run()
+    try:
+        N.check(N.lib().hicgat_gat_set_tuning(rows, l2_mb), "hicgat_gat_set_tuning")
+        got = run()
+    finally:
+        N.check(N.lib().hicgat_gat_set_tuning(8, 0), "hicgat_gat_set_tuning")
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert N.lib().hicgat_gat_set_tuning(12, 0) != 0 and N.lib().hicgat_gat_set_tuning(8, -1) != 0
+
+
 def test_gat_at_c4_size_paths_agree_and_forward_matches_oracle():
     """BASELINE.json config 4 size (9 970 loci, ~7 % density, 7 M edges): the CSR warp-per-row path and the
     dense-tile path must agree on output and every gradient, and the forward must match the oracle's
