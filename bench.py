@@ -628,7 +628,7 @@ def measure_workload(env: Env, name: str, primary: bool):
     # The kernel is bracketed by CUDA events INSIDE the timed region, but only on every EVERY-th step: an event record between two
     # launches costs a few microseconds of stream time and breaks their programmatic (PDL) chaining, which at 8 GPUs (0.2 ms steps)
     # would be 5 % of the number being measured.
-    EVERY = 1 if K < 32 else 8
+    EVERY = 1 if K < 8 else (4 if K < 32 else 8)
     sampled = [k for k in range(K) if k % EVERY == 0]
     ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for k in sampled}
     ev_end = {k: torch.cuda.Event(enable_timing=True) for k in sampled}
@@ -1026,7 +1026,7 @@ def run_native(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": ("pairloss_tma_kernel" if args.variant == 0 else "pairloss_ldg_kernel") + " + pairloss_combine_kernel", "kernel_ms": kern_ms,
                          "kernel_samples": res["kernel_samples"],
-                         "note": "kernel_ms = CUDA events around the two launches of one loss evaluation, on every 8th step of the timed region; peak is a COPY bandwidth (half reads, half writes): a read-only stream can exceed it slightly; "
+                         "note": "kernel_ms = CUDA events around the two launches of one loss evaluation, on every 4th (K < 32) or 8th step of the timed region; peak is a COPY bandwidth (half reads, half writes): a read-only stream can exceed it slightly; "
                                  "traffic = dram bytes of the committed ncu capture of this shape (profiles/pairloss_traffic.json), not re-measured in this run",
                          "algorithmic_bytes": res["alg_bytes"], "streamed_bytes": res["streamed_bytes"],
                          "streamed_note": "upper-triangle mode: the target is symmetric, the kernel reads ~2 B per ordered pair (column >= row only) and evaluates every unordered pair once; "
