@@ -28,6 +28,7 @@ SIGNATURES = {
     "hicgat_pairloss_fwd_bwd": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _p, _sz, _p]),
     "hicgat_pairloss_fwd_bwd_packed": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _u32, _f32, _f32, _p, _p, _sz, _p]),
     "hicgat_pairloss_set_tuning": (C.c_int, [_i32, _i32]),
+    "hicgat_pairloss_set_combine": (C.c_int, [_i32, _i32]),
     "hicgat_pairloss_set_schedule": (C.c_int, [_i32, _i32]),
     "hicgat_pairloss_describe_schedule": (C.c_int, [_i64, _i64, _i64, _p, _i32]),
     "hicgat_pairloss_describe_schedule_mode": (C.c_int, [_i64, _i64, _i64, _u32, _p, _i32]),
@@ -127,6 +128,13 @@ def set_pairloss_schedule(tail_depth: int = -1, tail_min_rows: int = 256) -> Non
     """``hicgat_pairloss_set_schedule`` + invalidation of the cached workspaces."""
     global _tuning_epoch
     check(lib().hicgat_pairloss_set_schedule(tail_depth, tail_min_rows), "hicgat_pairloss_set_schedule")
+    _tuning_epoch += 1
+
+
+def set_pairloss_combine(rowside_groups_max: int = 4, rowside_min_strips: int = 96) -> None:
+    """``hicgat_pairloss_set_combine`` + invalidation of the cached workspaces (their size depends on it)."""
+    global _tuning_epoch
+    check(lib().hicgat_pairloss_set_combine(rowside_groups_max, rowside_min_strips), "hicgat_pairloss_set_combine")
     _tuning_epoch += 1
 
 

@@ -246,6 +246,11 @@ struct Params {
     // one per warp; the partial of (strip s, warp w) lives in slot (w - first_warp(s)) * nstrips + s
     int64_t seg_len, seg_total;
     int seg_sa, seg_sb, seg_f;   // closed form of the rows per strip, see strip_offset()
+    // combine kernel, upper-triangle mode on a short row block: the row-side sums of the rs_count strips that hold this block's loci
+    // are cut into rs_groups segments of source strips, one CTA each (see pairloss_combine_kernel); rs_groups <= 1 = one CTA per strip
+    int rs_first, rs_count, rs_groups;
+    double* rs_scratch;       // [rs_count][rs_groups][384] segment sums
+    unsigned* rs_ticket;      // [rs_count] arrival counters, zero between calls
 };
 
 struct ColumnRegs {
@@ -495,12 +500,47 @@ constexpr int kCombineThreads = 512;
 // the buffers hold, stores nothing, and leaves the instruction cache, the TLB entries and the parameter
 // loads warm; pass 1 follows the wait (moment block of a 1 560-partial grid: 8.6 -> 5.4 us after the wait,
 // %globaltimer stamps; the gradient blocks did not change).
-__global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const Params P, const float scale, const int want_grad, const int npass) {
+// Sum of `count` partials src[k * stride] in index order, in f64, B loads per round.  Every load is issued UNCONDITIONALLY (the
+// index is clamped, the out-of-range term is replaced by +0.0 afterwards, which leaves the sum unchanged) so that the compiler keeps
+// all B in flight before the first add: with a bounds predicate per load it interleaves loads and adds, and the chain of dependent-
+// latency rounds -- which is all this kernel consists of on a short row block -- gets several times longer.
+template <int B>
+__device__ __forceinline__ double ordered_sum(const float* src, size_t stride, int count) {
+    double sum = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < count; c += B) {
+        float v[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) v[k] = __ldcg(src + (size_t)min(c + k, count - 1) * stride);
+#pragma unroll
+        for (int k = 0; k < B; ++k) sum += c + k < count ? (double)v[k] : 0.0;
+    }
+    return sum;
+}
+// column-side sum of one element of a strip: its per-CTA partials in chunk order
+__device__ __forceinline__ double colside_sum(const Params& P, int strip, int tid) {
+    return ordered_sum<8>(P.gpart + (size_t)strip * (kCols * 3) + tid, (size_t)P.nstrips * (kCols * 3), active_chunks(P, strip));
+}
+// row-side sum of one element over the source strips [s_begin, s_end), in strip order
+__device__ __forceinline__ double rowside_sum(const Params& P, const float* rsrc, int s_begin, int s_end) {
+    return ordered_sum<16>(rsrc + (size_t)s_begin * P.rpitch, (size_t)P.rpitch, s_end - s_begin);
+}
+
+// Grid: [rs_count * rs_groups row-side CTAs (only when rs_groups > 1)] [nstrips gradient CTAs] [1 moment CTA].
+// Row-side CTAs: a thread sums ONE element over up to nstrips source strips, a chain of dependent-latency rounds (16 loads each).  On
+// a short row block (a shard of a sharded run) only a handful of strips hold loci of the block, so that chain -- not bandwidth -- is
+// the whole kernel: each such strip is therefore cut into rs_groups segments of source strips, one CTA each; the CTA that arrives
+// last at the strip's ticket adds the segment sums in segment order (and the column-side sum) and writes the gradient.  Every sum
+// has a fixed order, so the result does not depend on which CTA arrives last: bit-reproducible.
+__global__ void __launch_bounds__(kCombineThreads, 2) pairloss_combine_kernel(const Params P, const float scale, const int want_grad, const int npass) {
     pdl_launch_dependents();  // a consumer launched with programmatic serialization (the sharded exchange kernel) may become resident now
     const int tid = threadIdx.x;
     __shared__ double s_m[kCombineThreads / 32][kNM];
+    __shared__ int s_last;
+    const int G = P.rs_groups > 1 ? P.rs_groups : 0;
+    const int bid = (int)blockIdx.x - G * P.rs_count;   // < 0: row-side CTA; [0, nstrips): gradient CTA of a strip; nstrips: moments
 #ifdef HICGAT_TRACE
-    unsigned long long* ctr = (g_trace && tid == 0 && ((int)blockIdx.x == 0 || (int)blockIdx.x == P.nstrips)) ? g_trace + (size_t)(8190 + ((int)blockIdx.x == 0 ? 0 : 1)) * 8 : nullptr;
+    unsigned long long* ctr = (g_trace && tid == 0 && (bid == 0 || bid == P.nstrips)) ? g_trace + (size_t)(8190 + (bid == 0 ? 0 : 1)) * 8 : nullptr;
     if (ctr) ctr[0] = gtimer();
 #endif
 #pragma unroll 1
@@ -508,40 +548,54 @@ __global__ void __launch_bounds__(kCombineThreads) pairloss_combine_kernel(const
         const bool live = pass == npass - 1;
         if (live) {
             pdl_wait();  // no-op when launched without the programmatic-serialization attribute
-            if (P.work_counter && blockIdx.x == 0 && tid == 0) *P.work_counter = 0u;  // the persistent kernel's item counter, for the next launch
+            if (P.work_counter && bid == 0 && tid == 0) *P.work_counter = 0u;  // the persistent kernel's item counter, for the next launch
 #ifdef HICGAT_TRACE
             if (ctr) ctr[1] = gtimer();
 #endif
         }
-        if ((int)blockIdx.x < P.nstrips) {
+        if (bid < 0) {
             if (!want_grad) return;
-            const int strip = blockIdx.x;
-            const int count = active_chunks(P, strip);
-            // one element of the strip's 384 per thread, 8 chunks per round: 8 independent loads in flight, added
-            // in chunk order (out-of-range terms are +0.0, which leaves the sum unchanged)
+            const int bi = (int)blockIdx.x / G, g = (int)blockIdx.x - bi * G;
+            const int strip = P.rs_first + bi;
+            const int locus = strip * kCols + tid / 3;
             if (tid < kCols * 3) {
-                const float* src = P.gpart + (size_t)strip * (kCols * 3) + tid;
-                const size_t stride = (size_t)P.nstrips * (kCols * 3);
-                double sum = 0.0;
-                for (int c = 0; c < count; c += 8) {
-                    float v[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) v[k] = c + k < count ? __ldcg(src + (size_t)(c + k) * stride) : 0.f;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) sum += (double)v[k];
+                double part = 0.0;
+                if (locus >= P.r0 && locus < P.r1) {
+                    const int len = (P.nstrips - strip + G - 1) / G;
+                    const int sb = strip + g * len, se = min(sb + len, P.nstrips);
+                    part = rowside_sum(P, P.rpart + (size_t)(locus - P.r0) * 3 + (tid - (tid / 3) * 3), sb, se);
                 }
-                const int locus = strip * kCols + tid / 3;
-                if (P.upper && locus >= P.r0 && locus < P.r1) {
-                    // row-side sums of this locus: one partial per strip at or right of its own, added in strip order
-                    const float* rsrc = P.rpart + (size_t)(locus - P.r0) * 3 + (tid - (tid / 3) * 3);
-                    for (int s0 = strip; s0 < P.nstrips; s0 += 16) {
-                        float v[16];
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) v[k] = s0 + k < P.nstrips ? __ldcg(rsrc + (size_t)(s0 + k) * P.rpitch) : 0.f;
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) sum += (double)v[k];
+                if (live) P.rs_scratch[((size_t)bi * G + g) * (kCols * 3) + tid] = part;
+            }
+            if (live) {
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) s_last = atomicAdd(P.rs_ticket + bi, 1u) == (unsigned)(G - 1) ? 1 : 0;
+                __syncthreads();
+                if (s_last) {
+                    __threadfence();
+                    if (tid < kCols * 3) {
+                        double sum = colside_sum(P, strip, tid);
+                        for (int g2 = 0; g2 < G; ++g2) sum += __ldcg(P.rs_scratch + ((size_t)bi * G + g2) * (kCols * 3) + tid);
+                        if (locus < P.n) {
+                            const double val = sum * (double)scale;
+                            if (P.grad) P.grad[(size_t)strip * kCols * 3 + tid] = (float)val;
+                            if (P.grad64) P.grad64[(size_t)strip * kCols * 3 + tid] = (double)(float)val;
+                        }
                     }
+                    if (tid == 0) P.rs_ticket[bi] = 0u;  // for the next call
                 }
+            }
+        } else if (bid < P.nstrips) {
+            if (!want_grad) return;
+            const int strip = bid;
+            if (G && strip >= P.rs_first && strip < P.rs_first + P.rs_count) return;  // written by the strip's row-side CTAs
+            // one element of the strip's 384 per thread
+            if (tid < kCols * 3) {
+                double sum = colside_sum(P, strip, tid);
+                const int locus = strip * kCols + tid / 3;
+                if (P.upper && locus >= P.r0 && locus < P.r1)  // row-side sums of this locus: one partial per strip at or right of its own
+                    sum += rowside_sum(P, P.rpart + (size_t)(locus - P.r0) * 3 + (tid - (tid / 3) * 3), strip, P.nstrips);
                 if (live && locus < P.n) {
                     const double val = sum * (double)scale;
                     if (P.grad) P.grad[(size_t)strip * kCols * 3 + tid] = (float)val;
@@ -1389,7 +1443,34 @@ struct Layout {
     int item_base[kMaxChunks + 1];
     int64_t seg_len, seg_total;  // variant 4: static warp partition (seg_len = 0 otherwise)
     int seg_sa, seg_sb, seg_f, seg_warps;
+    int rs_first, rs_count, rs_groups;       // combine kernel: segmented row-side sums (upper-triangle mode, short row blocks)
+    size_t off_rs_ticket, off_rs_scratch;
 };
+
+int g_rs_groups_max = 4;  // hicgat_pairloss_set_combine: 1 = one combine CTA per strip (no segments)
+int g_rs_min_strips = 96; // shortest segment worth a CTA of its own (measured on 1/8 .. 1/2 blocks of a 390-strip map: chains of
+                          // 390 / 338 strips gain 10 % / 3 % of the whole loss evaluation from 4 / 3 segments, a 138-strip chain loses 2 %)
+
+// Upper-triangle mode: how many CTAs share the row-side sums of one strip of this block's loci (see pairloss_combine_kernel), and
+// the workspace behind it.  At most one wave of row-side CTAs (2 per SM) and g_rs_groups_max segments of at least g_rs_min_strips strips.
+void add_rowside_layout(Layout& L, int64_t r0, int64_t r1, bool sym) {
+    L.rs_first = 0;
+    L.rs_count = 0;
+    L.rs_groups = 1;
+    L.off_rs_ticket = L.off_rs_scratch = L.total;
+    if (!sym || r1 <= r0) return;
+    L.rs_first = (int)(r0 / kCols);
+    L.rs_count = (int)((r1 - 1) / kCols) - L.rs_first + 1;
+    int g = std::min((2 * 148) / L.rs_count, g_rs_groups_max);
+    const int longest = L.nstrips - L.rs_first;
+    while (g > 1 && (longest + g - 1) / g < g_rs_min_strips) --g;
+    L.rs_groups = std::max(g, 1);
+    if (L.rs_groups > 1) {
+        L.off_rs_ticket = align_up(L.total, 256);
+        L.off_rs_scratch = L.off_rs_ticket + align_up(sizeof(unsigned) * (size_t)L.rs_count, 256);
+        L.total = L.off_rs_scratch + sizeof(double) * (size_t)L.rs_count * L.rs_groups * kCols * 3;
+    }
+}
 
 int g_tail_depth = -1;    // -1 = library default; >= 0: hicgat_pairloss_set_schedule
 int g_tail_min_rows = 256;
@@ -1510,6 +1591,7 @@ Layout make_layout_uncached(int64_t n, int64_t r0, int64_t r1, int variant, bool
         L.rpitch = sym ? (int64_t)align_up((size_t)nrows * 3, 32) : 0;
         L.off_counter = align_up(L.off_rpart + sizeof(float) * (size_t)L.rpitch * L.nstrips, 256);
         L.total = L.off_counter + 256;
+        add_rowside_layout(L, r0, r1, sym);
         return L;
     }
     if (variant == 3 || variant == 4) variant = 0;  // same tiles / partial layout as the TMA kernel
@@ -1597,6 +1679,7 @@ Layout make_layout_uncached(int64_t n, int64_t r0, int64_t r1, int variant, bool
     L.rpitch = sym ? (int64_t)align_up((size_t)(nrows > 0 ? nrows : 1) * 3, 32) : 0;
     L.off_counter = align_up(L.off_rpart + sizeof(float) * (size_t)L.rpitch * L.nstrips, 256);
     L.total = L.off_counter + 256;
+    add_rowside_layout(L, r0, r1, sym);
     if (L.persistent) {
         for (int c = 0; c < L.sch.count[0]; ++c) {
             int first = 0;
@@ -1614,14 +1697,15 @@ Layout make_layout_uncached(int64_t n, int64_t r0, int64_t r1, int variant, bool
 Layout make_layout(int64_t n, int64_t r0, int64_t r1, int variant, bool sym = false) {
     struct Key {
         int64_t n, r0, r1;
-        int variant, sym, rows, stagger, depth, tail_min;
+        int variant, sym, rows, stagger, depth, tail_min, rs_max, rs_min;
         bool operator<(const Key& o) const {
-            return std::tie(n, r0, r1, variant, sym, rows, stagger, depth, tail_min) < std::tie(o.n, o.r0, o.r1, o.variant, o.sym, o.rows, o.stagger, o.depth, o.tail_min);
+            return std::tie(n, r0, r1, variant, sym, rows, stagger, depth, tail_min, rs_max, rs_min) <
+                   std::tie(o.n, o.r0, o.r1, o.variant, o.sym, o.rows, o.stagger, o.depth, o.tail_min, o.rs_max, o.rs_min);
         }
     };
     static std::mutex mu;
     static std::map<Key, Layout> cache;
-    const Key key{n, r0, r1, variant, sym ? 1 : 0, g_rows_per_cta, g_stagger, g_tail_depth, g_tail_min_rows};
+    const Key key{n, r0, r1, variant, sym ? 1 : 0, g_rows_per_cta, g_stagger, g_tail_depth, g_tail_min_rows, g_rs_groups_max, g_rs_min_strips};
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
@@ -1665,7 +1749,7 @@ cudaError_t launch_combine(const Params& P, cudaStream_t stream) {
     const int want_grad = (MODE & 3u) != 0 ? 1 : 0;
     if (g_pdl) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(P.nstrips + 1);
+        cfg.gridDim = dim3(P.nstrips + 1 + (P.rs_groups > 1 ? P.rs_groups * P.rs_count : 0));
         cfg.blockDim = dim3(kCombineThreads);
         cfg.dynamicSmemBytes = 0;
         cfg.stream = stream;
@@ -1676,7 +1760,7 @@ cudaError_t launch_combine(const Params& P, cudaStream_t stream) {
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, pairloss_combine_kernel, P, scale, want_grad, 2);
     }
-    pairloss_combine_kernel<<<P.nstrips + 1, kCombineThreads, 0, stream>>>(P, scale, want_grad, 1);
+    pairloss_combine_kernel<<<P.nstrips + 1 + (P.rs_groups > 1 ? P.rs_groups * P.rs_count : 0), kCombineThreads, 0, stream>>>(P, scale, want_grad, 1);
     return cudaGetLastError();
 }
 
@@ -1784,6 +1868,16 @@ extern "C" __attribute__((visibility("default"))) int hicgat_debug_set_trace(uns
     return cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
 }
 #endif
+
+extern "C" int hicgat_pairloss_set_combine(int rowside_groups_max, int rowside_min_strips) {
+    if (rowside_groups_max < 1 || rowside_groups_max > 16 || rowside_min_strips < 1) {
+        set_error("hicgat_pairloss_set_combine: rowside_groups_max must be in [1,16], rowside_min_strips >= 1");
+        return HICGAT_ERR_INVALID;
+    }
+    g_rs_groups_max = rowside_groups_max;
+    g_rs_min_strips = rowside_min_strips;
+    return HICGAT_OK;
+}
 
 extern "C" int hicgat_pairloss_set_tuning(int rows_per_cta, int variant) {
     if (rows_per_cta != 0 && (rows_per_cta < 8 || rows_per_cta > 4096 || (rows_per_cta % 8) != 0)) {
@@ -1914,6 +2008,11 @@ static int pairloss_impl(const float* coords, const float* target, int64_t pitch
         memcpy(P.item_base, L.item_base, sizeof(P.item_base));
         if (!ws_clean) HICGAT_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned), stream));
     }
+    P.rs_first = L.rs_first; P.rs_count = L.rs_count; P.rs_groups = L.rs_groups;
+    P.rs_ticket = reinterpret_cast<unsigned*>(ws + L.off_rs_ticket);
+    P.rs_scratch = reinterpret_cast<double*>(ws + L.off_rs_scratch);
+    // the tickets return to zero at the end of every call; a workspace of unknown content is cleared first
+    if (L.rs_groups > 1 && !ws_clean) HICGAT_CUDA(cudaMemsetAsync(P.rs_ticket, 0, sizeof(unsigned) * (size_t)L.rs_count, stream));
     dim3 grid(L.nstrips, L.nchunks);
     cudaError_t err = cudaSuccess;
     switch (mode) {
@@ -2028,6 +2127,10 @@ static int pairloss_sparse_impl(const float* coords, const int32_t* rowptr, cons
     P.upper = sym ? 1 : 0; P.rpitch = L.dense.rpitch; P.rpart = reinterpret_cast<float*>(ws + L.dense.off_rpart);
     P.work_counter = nullptr; P.nitems = 0;
     P.seg_len = 0; P.seg_total = 0; P.seg_sa = P.seg_sb = P.seg_f = 0;
+    P.rs_first = L.dense.rs_first; P.rs_count = L.dense.rs_count; P.rs_groups = L.dense.rs_groups;
+    P.rs_ticket = reinterpret_cast<unsigned*>(ws + L.dense.off_rs_ticket);
+    P.rs_scratch = reinterpret_cast<double*>(ws + L.dense.off_rs_scratch);
+    if (L.dense.rs_groups > 1 && !ws_clean) HICGAT_CUDA(cudaMemsetAsync(P.rs_ticket, 0, sizeof(unsigned) * (size_t)L.dense.rs_count, stream));
     dim3 grid(L.dense.nstrips, L.dense.nchunks);
     double* part = reinterpret_cast<double*>(ws + L.off_part);
     unsigned* counter = reinterpret_cast<unsigned*>(ws + L.off_counter);

@@ -133,6 +133,11 @@ HICGAT_API int hicgat_pairloss_set_tuning(int rows_per_cta, int variant);
  * that the CTAs dispatched last are short and the CTA slots run dry together.  tail_depth -1 = library
  * default, 0 = equal chunks. */
 HICGAT_API int hicgat_pairloss_set_schedule(int tail_depth, int tail_min_rows);
+/* Tuning hook (bench/tests): the combine kernel of the upper-triangle mode sums, per locus of the row block, one row-side partial
+ * per column strip -- a chain of dependent load rounds.  On short row blocks (shards) each strip of loci is therefore split into up
+ * to `rowside_groups_max` segments of at least `rowside_min_strips` source strips, one CTA each, joined in segment order by the CTA
+ * that arrives last (bit-reproducible).  Defaults 4 / 96; (1, any) = one CTA per strip.  Changes the workspace size: re-query. */
+HICGAT_API int hicgat_pairloss_set_combine(int rowside_groups_max, int rowside_min_strips);
 /* Introspection (tests): the row-chunk schedule the CURRENT tuning gives rows [r0, r1) of an n-locus map.
  * out = [nstrips, stagger, count0, count1, bounds0[0..count0], bounds1[0..count1]] (row offsets from r0; table 1
  * is used by the staggered strips).  Returns the number of ints written or a negative error code. */

@@ -446,6 +446,46 @@ def test_upper_triangle_row_blocks_sum_to_full(n, cuts, rb, variant):
         N.set_pairloss_tuning(0, 0)
 
 
+@pytest.mark.parametrize("n,cuts,groups,min_strips", [(3001, [0, 5, 1000, 1003, 3001], 8, 1), (3001, [0, 5, 1000, 1003, 3001], 5, 3), (777, [0, 200, 601, 777], 8, 1),
+                                                      (777, [0, 200, 601, 777], 2, 1), (1300, [130, 1290], 5, 3), (30000, [0, 1900], 4, 96), (30000, [2000, 4100], 4, 96)])
+def test_upper_triangle_segmented_combine_matches_one_cta_per_strip(n, cuts, groups, min_strips):
+    """``hicgat_pairloss_set_combine``: the row-side sums of a strip of loci cut into segments (one combine CTA each, joined by the
+    last arrival) against one CTA per strip: same moments bit for bit, gradients equal up to the order of the f64 adds; repeated
+    calls bit-identical (the tickets return to zero); a workspace of unknown content (no HICGAT_PAIR_WS_CLEAN) is cleared first."""
+    import hic_gnn_b200 as hg
+    from hic_gnn_b200 import _native as N
+    from hic_gnn_b200 import ops
+
+    coords = random_coords(n, seed=n).cuda()
+    g = torch.Generator().manual_seed(n)
+    mode = ops._MODES["mse_moments_full"]
+    try:
+        for r0, r1 in zip(cuts[:-1], cuts[1:]):
+            blk = hg.WishTarget.empty(n, r0, r1, symmetric=True)
+            blk.data[:, :n].copy_(torch.rand(r1 - r0, n, generator=g).cuda())
+            N.set_pairloss_combine(1, 96)
+            m1, g1 = (t.clone() for t in ops.pairloss_raw(coords, blk, mode, 4.0 / n**2, 0.0))
+            N.set_pairloss_combine(groups, min_strips)
+            m2, g2 = (t.clone() for t in ops.pairloss_raw(coords, blk, mode, 4.0 / n**2, 0.0))
+            m3, g3 = ops.pairloss_raw(coords, blk, mode, 4.0 / n**2, 0.0)
+            assert torch.equal(m1, m2) and torch.equal(m2, m3) and torch.equal(g2, g3)
+            assert rel_err(g2, g1) < 1e-6
+            # raw call, workspace filled with ones, no WS_CLEAN bit
+            lib = N.lib()
+            bits = mode | N.PAIR_SYMMETRIC
+            ws = torch.full((lib.hicgat_pairloss_workspace_bytes_mode(n, r0, r1, bits),), 1, dtype=torch.uint8, device="cuda")
+            m4 = torch.empty(N.PAIR_NMOM, dtype=torch.float64, device="cuda")
+            g4 = torch.empty(n, 3, dtype=torch.float32, device="cuda")
+            for _ in range(2):
+                N.check(lib.hicgat_pairloss_fwd_bwd(coords.data_ptr(), blk.data.data_ptr(), blk.pitch, n, r0, r1, bits, 4.0 / n**2, 0.0, m4.data_ptr(), g4.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "hicgat_pairloss_fwd_bwd")
+                assert torch.equal(m4, m2) and torch.equal(g4, g2)
+    finally:
+        N.set_pairloss_combine()
+    with pytest.raises(RuntimeError):
+        N.set_pairloss_combine(0, 24)
+
+
 @pytest.mark.parametrize("variant", [0, 3, 4])
 @pytest.mark.parametrize("n,cuts,rb", [(19500, [0, 100, 6016, 19500], 0), (19300, [0, 700, 19300], 128), (30000, [0, 30000], 0)])
 def test_upper_triangle_large_maps_match_full_matrix_kernel(n, cuts, rb, variant):
