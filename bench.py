@@ -537,29 +537,35 @@ def build_inputs(env: Env, name: str, want_graph: bool, want_cpu_rows: int):
     target = build_target(r0, r1)
     if balance == "upper" and env.world > 1 and n >= 4096 and not env.args.no_rebalance:
         # MEASURED load balancing (setup, outside every timed region): equal-area blocks do not take equal time, and the exchange waits
-        # for the slowest rank.  Two rounds of: time this rank's kernel, all-gather the times, move the cuts (sharding.rebalance_cuts).
+        # for the slowest rank.  Three rounds of: time this rank's kernel, all-gather the times, move the cuts (sharding.rebalance_cuts).
         g = torch.Generator().manual_seed(7)
         c_probe = (0.3 * torch.randn(n, 3, generator=g)).to(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(2):
+        ROUNDS = 3
+        for it in range(ROUNDS + 1):
             for _w in range(3):
                 ops.pairloss_raw(c_probe, target, ops._MODES["mse"], 4.0 / n**2, 0.0)
             env.barrier()
             e0.record()
-            for _w in range(10):
+            for _w in range(20):
                 ops.pairloss_raw(c_probe, target, ops._MODES["mse"], 4.0 / n**2, 0.0)
             e1.record()
             e1.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+            t = torch.tensor([e0.elapsed_time(e1) / 20], dtype=torch.float64, device=dev)
             times = [torch.zeros_like(t) for _ in range(env.world)]
             env.dist.all_gather(times, t)
             times = [float(x) for x in times]
             rebalanced.append({"cuts": list(cuts), "kernel_ms": [round(x, 4) for x in times]})
-            cuts = sharding.rebalance_cuts(n, cuts, times)
-            r0, r1 = cuts[rank_eff], cuts[rank_eff + 1]
-            del target
-            torch.cuda.empty_cache()
-            target = build_target(r0, r1)
+            if it < ROUNDS:
+                new_cuts = sharding.rebalance_cuts(n, cuts, times)
+            else:  # the model is piecewise linear, the kernel's schedule is not: keep the best partition that was MEASURED
+                new_cuts = min(rebalanced, key=lambda h: max(h["kernel_ms"]))["cuts"]
+            if list(new_cuts) != list(cuts):
+                cuts = list(new_cuts)
+                r0, r1 = cuts[rank_eff], cuts[rank_eff + 1]
+                del target
+                torch.cuda.empty_cache()
+                target = build_target(r0, r1)
         del c_probe
     graph = None
     if want_graph:
