@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # float(loss) on a tensor that still carries a graph is what the assertions mean to do
+    config.addinivalue_line("filterwarnings", "ignore:Converting a tensor with requires_grad=True to a scalar:UserWarning")
 
 
 @pytest.fixture(scope="session")

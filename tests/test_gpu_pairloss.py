@@ -223,7 +223,7 @@ def test_full_size_closed_form_properties(n):
     loss, m = hg.pairwise_loss(c, tgt, "mse_moments")
     (g,) = torch.autograd.grad(loss, c)
     mean_t2 = float((t.double() ** 2).mean())
-    assert abs(float(loss) - (s - 1) ** 2 * mean_t2) / ((s - 1) ** 2 * mean_t2) < TOL
+    assert abs(float(loss.detach()) - (s - 1) ** 2 * mean_t2) / ((s - 1) ** 2 * mean_t2) < TOL
     # dL/ds = 2 (s-1) mean(t^2)  and  dL/ds = <grad, y>
     assert abs(float((g.double() * y.double()).sum()) - 2 * (s - 1) * mean_t2) / (2 * (s - 1) * mean_t2) < TOL
     assert abs(float(pearson_from_moments(m, n * (n - 1) / 2)) - 1.0) < 1e-6
