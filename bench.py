@@ -766,9 +766,13 @@ def measure_workload(env: Env, name: str, primary: bool):
         e_ms = max_over_ranks(start.elapsed_time(stop))
         h2d = max_over_ranks(float(hp.h2d_bytes))
         assert abs(float(hm[0]) - float(moments[0])) <= 1e-5 * abs(float(moments[0])), (float(hm[0]), float(moments[0]))
+        # the host-buffer path walks ~1 300-row blocks (another schedule, the segmented combine): its gradient must be the resident one
+        g_res = grad.detach().double().cpu().reshape(n, 3)
+        e2e_grad_err = float((hgrad.double() - g_res).abs().max() / g_res.abs().max().clamp(min=1e-300))
+        assert e2e_grad_err < 1e-5, e2e_grad_err
         e2e = {"value": float(n) * float(n) * Ke / (e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(hp.d2h_bytes), "steps": Ke, "ms_per_step": e_ms / Ke,
-               "h2d_gbs": h2d / (e_ms / Ke * 1e-3) / 1e9,
+               "h2d_gbs": h2d / (e_ms / Ke * 1e-3) / 1e9, "grad_rel_err_vs_resident": e2e_grad_err,
                "note": "per rank: coords + this rank's f32 target rows from pinned host memory every step (PCIe-bound by construction)"
                        + ("; the target is symmetric, so only the columns at or right of each row block's diagonal are copied" if upper else "")}
         del host_target, hp
