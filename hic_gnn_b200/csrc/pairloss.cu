@@ -526,7 +526,7 @@ __device__ __forceinline__ double rowside_sum(const Params& P, const float* rsrc
     return ordered_sum<16>(rsrc + (size_t)s_begin * P.rpitch, (size_t)P.rpitch, s_end - s_begin);
 }
 
-// Grid: [rs_count * rs_groups row-side CTAs (only when rs_groups > 1)] [nstrips gradient CTAs] [1 moment CTA].
+// Grid: [1 moment CTA] [rs_count * rs_groups row-side CTAs (only when rs_groups > 1)] [nstrips gradient CTAs].
 // Row-side CTAs: a thread sums ONE element over up to nstrips source strips, a chain of dependent-latency rounds (16 loads each).  On
 // a short row block (a shard of a sharded run) only a handful of strips hold loci of the block, so that chain -- not bandwidth -- is
 // the whole kernel: each such strip is therefore cut into rs_groups segments of source strips, one CTA each; the CTA that arrives
@@ -538,7 +538,10 @@ __global__ void __launch_bounds__(kCombineThreads, 2) pairloss_combine_kernel(co
     __shared__ double s_m[kCombineThreads / 32][kNM];
     __shared__ int s_last;
     const int G = P.rs_groups > 1 ? P.rs_groups : 0;
-    const int bid = (int)blockIdx.x - G * P.rs_count;   // < 0: row-side CTA; [0, nstrips): gradient CTA of a strip; nstrips: moments
+    // Block 0 sums the moments: its chain of dependent rounds is as long as a row-side CTA's, so it must not wait for a free slot
+    // behind the (more than one wave of) gradient CTAs.  Then the row-side CTAs (longest), then one gradient CTA per strip.
+    const int rs_idx = (int)blockIdx.x - 1;                                      // row-side CTA index when 0 <= rs_idx < G * rs_count
+    const int bid = blockIdx.x == 0 ? P.nstrips : rs_idx - G * P.rs_count;       // < 0: row-side CTA; [0, nstrips): strip; nstrips: moments
 #ifdef HICGAT_TRACE
     unsigned long long* ctr = (g_trace && tid == 0 && (bid == 0 || bid == P.nstrips)) ? g_trace + (size_t)(8190 + (bid == 0 ? 0 : 1)) * 8 : nullptr;
     if (ctr) ctr[0] = gtimer();
@@ -555,7 +558,7 @@ __global__ void __launch_bounds__(kCombineThreads, 2) pairloss_combine_kernel(co
         }
         if (bid < 0) {
             if (!want_grad) return;
-            const int bi = (int)blockIdx.x / G, g = (int)blockIdx.x - bi * G;
+            const int bi = rs_idx / G, g = rs_idx - bi * G;
             const int strip = P.rs_first + bi;
             const int locus = strip * kCols + tid / 3;
             if (tid < kCols * 3) {
