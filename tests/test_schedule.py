@@ -78,3 +78,32 @@ def test_schedule_argument_validation():
     buf = (C.c_int32 * 4)()
     assert lib.hicgat_pairloss_describe_schedule(9970, 0, 9970, C.addressof(buf), 4) == -3  # capacity too small
     assert lib.hicgat_pairloss_describe_schedule(0, 0, 0, C.addressof(buf), 4) == -1
+
+
+def test_segmented_combine_workspace_and_validation():
+    """``hicgat_pairloss_set_combine`` (host logic only): segments of the row-side sums need ticket + scratch space only for
+    upper-triangle blocks whose strip chain is long enough; (1, x) switches them off; bad arguments are refused."""
+    lib = N.lib()
+    n = 49850
+    sym = N.PAIR_SYMMETRIC
+
+    def ws(r0, r1, mode):
+        return lib.hicgat_pairloss_workspace_bytes_mode(n, r0, r1, mode)
+
+    try:
+        N.set_pairloss_combine(1, 96)
+        base_shard, base_full, base_tail, base_plain = ws(0, 3200, sym), ws(0, n, sym), ws(32256, n, sym), ws(0, 3200, 0)
+        N.set_pairloss_combine(4, 96)
+        # rows 0..3199 = 25 strips of loci, chains of up to 390 strips: 4 segments -> 25 tickets + 25 * 4 * 384 f64
+        assert ws(0, 3200, sym) - base_shard >= 25 * 4 * 384 * 8
+        assert ws(0, 3200, sym) - base_shard <= 25 * 4 * 384 * 8 + 4096
+        assert ws(0, n, sym) == base_full          # 390 strips of loci: more than one wave already, no segments
+        assert ws(32256, n, sym) == base_tail      # chains of at most 138 strips: shorter than one 96-strip segment pair
+        assert ws(0, 3200, 0) == base_plain        # full-matrix mode has no row-side sums
+        N.set_pairloss_combine(8, 1)
+        assert ws(32256, n, sym) > base_tail
+        for bad in ((0, 96), (17, 96), (4, 0)):
+            assert lib.hicgat_pairloss_set_combine(*bad) != 0
+            assert b"set_combine" in lib.hicgat_last_error()
+    finally:
+        N.set_pairloss_combine()
